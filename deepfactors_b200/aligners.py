@@ -1,0 +1,334 @@
+"""Host-side mirror of the reference's aligner API over libdfk.so.
+
+Same class / method names, argument order and result types as
+  df::SfmAligner<float,CS>   sources/cuda/cu_sfmaligner.h:50-97
+  df::SE3Aligner<float>      sources/cuda/cu_se3aligner.h:38-86
+  df::UpdateDepth / SobelGradients / GaussianBlurDown / SquaredError   sources/cuda/cu_image_proc.h:27-44
+  df::JTJJrReductionItem / CorrespondenceReductionItem                  sources/cuda/reduction_items.h:35-143
+(the C++ facade with the real template signatures is include/df/*.h; this module exists so the
+parity tests and the benchmark can drive the C ABI from Python).  Image arguments are torch CUDA
+float32 tensors standing in for vc::Image2DView<float, TargetDeviceCUDA>: [H, W] scalar images,
+[H, W, 2] gradients, [H, W, C] code Jacobians; the row stride may exceed the row length (pitched).
+
+PyTorch is plumbing only (device memory + streams).  Every computation is a libdfk.so call; there
+is no CPU or torch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DfkCamera, DfkDenseSfmParams, DfkImage, DfkSfmAlignerParams, DfkSfmWorkItem, check, lib
+
+
+# ------------------------------------------------------------------------------------------- params
+@dataclass
+class DenseSfmParams:
+    """df::DenseSfmParams (sources/common/algorithm/dense_sfm.h:36-43)."""
+    huber_delta: float = 0.1
+    ocl_th: float = 1000.0
+    avg_dpt: float = 2.0
+    min_dpt: float = 0.0
+    valid_border: int = 2
+
+
+@dataclass
+class SfmAlignerParams:
+    """df::SfmAlignerParams (sources/cuda/cu_sfmaligner.h:41-48)."""
+    sfmparams: DenseSfmParams = field(default_factory=DenseSfmParams)
+    step_threads: int = 32
+    step_blocks: int = 11
+    eval_threads: int = 224
+    eval_blocks: int = 66
+
+    def to_c(self) -> DfkSfmAlignerParams:
+        s = self.sfmparams
+        return DfkSfmAlignerParams(DfkDenseSfmParams(s.huber_delta, s.ocl_th, s.avg_dpt, s.min_dpt, s.valid_border),
+                                   self.step_threads, self.step_blocks, self.eval_threads, self.eval_blocks)
+
+
+# ------------------------------------------------------------------------------------------- results
+@dataclass
+class CorrespondenceReductionItem:
+    """sources/cuda/reduction_items.h:35-71"""
+    residual: float = 0.0
+    inliers: int = 0
+
+
+@dataclass
+class JTJJrReductionItem:
+    """sources/cuda/reduction_items.h:77-143.  JtJ is the packed upper triangle (row major)."""
+    JtJ: np.ndarray
+    Jtr: np.ndarray
+    residual: float
+    inliers: int
+
+    @property
+    def NP(self) -> int:
+        return int(self.Jtr.shape[0])
+
+    def toDenseMatrix(self) -> np.ndarray:
+        """SquareUpperTriangularMatrix::toDenseMatrix(): full symmetric NP x NP."""
+        n = self.NP
+        H = np.zeros((n, n), dtype=self.JtJ.dtype)
+        H[np.triu_indices(n)] = self.JtJ
+        return H + np.triu(H, 1).T
+
+    @staticmethod
+    def from_record(rec: np.ndarray, code_size: int) -> "JTJJrReductionItem":
+        n = 12 + code_size
+        nh = n * (n + 1) // 2
+        rec = np.ascontiguousarray(rec, dtype=np.float32)
+        inl = int(rec[nh + n + 1:nh + n + 2].view(np.uint32)[0])
+        return JTJJrReductionItem(rec[:nh].copy(), rec[nh:nh + n].copy(), float(rec[nh + n]), inl)
+
+
+# ------------------------------------------------------------------------------------------- views
+def _image(t: torch.Tensor, floats_per_px: int = 1) -> DfkImage:
+    """vc::Image2DView over a torch CUDA tensor (no copy)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32:
+        raise TypeError("expected a float32 CUDA tensor")
+    if floats_per_px == 1:
+        if t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError("scalar image must be [H, W] with unit column stride")
+    else:
+        if t.dim() == 3:
+            if t.shape[2] != floats_per_px or t.stride(2) != 1 or t.stride(1) != floats_per_px:
+                raise ValueError("interleaved image must be [H, W, K] with contiguous pixels")
+        elif t.dim() == 2:  # the reference's (W*K) x H float-image view
+            if t.shape[1] % floats_per_px != 0 or t.stride(1) != 1:
+                raise ValueError("flat interleaved image must be [H, W*K]")
+        else:
+            raise ValueError("bad image rank")
+    h = t.shape[0]
+    w = t.shape[1] if (t.dim() == 3 or floats_per_px == 1) else t.shape[1] // floats_per_px
+    return DfkImage(C.c_void_p(t.data_ptr()), t.stride(0) * 4, w, h)
+
+
+def _cam(cam) -> DfkCamera:
+    return DfkCamera(cam.fx, cam.fy, cam.u0, cam.v0, cam.width, cam.height)
+
+
+def _pose(p) -> "C.Array":
+    a = np.ascontiguousarray(np.asarray(p, dtype=np.float32))
+    if a.shape != (7,):
+        raise ValueError("pose must be 7 floats: quaternion (x,y,z,w), translation")
+    return (C.c_float * 7)(*a.tolist())
+
+
+class _Handle:
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("deepfactors_b200 needs a CUDA device (no CPU fallback)")
+        dev = torch.cuda.current_device() if device is None else torch.device(device).index
+        self.device = dev if dev is not None else torch.cuda.current_device()
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device="cuda")  # make sure the primary context exists
+        self.h = C.c_void_p()
+        st = lib().dfk_create(int(self.device), C.byref(self.h))
+        if st != _lib.DFK_OK:
+            raise _lib.DfkError(st, "dfk_create failed")
+
+    def use_torch_stream(self):
+        """launch on torch's current stream (so torch-side events and allocations order correctly)"""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        check(self.h, lib().dfk_set_stream(self.h, C.c_void_p(s)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            lib().dfk_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------- SfmAligner
+class SfmAligner:
+    """df::SfmAligner<float, CS> (sources/cuda/cu_sfmaligner.h:50-97)."""
+
+    def __init__(self, code_size: int, params: SfmAlignerParams | None = None, device=None, gram_mode: str = "auto"):
+        self.CS = int(code_size)
+        self.params_ = params or SfmAlignerParams()
+        self._hd = _Handle(device)
+        self._hd.use_torch_stream()
+        cp = self.params_.to_c()
+        check(self._hd.h, lib().dfk_sfm_set_params(self._hd.h, C.byref(cp)))
+        self.SetGramMode(gram_mode)
+
+    @property
+    def handle(self):
+        return self._hd.h
+
+    def SetGramMode(self, mode: str):
+        m = {"auto": _lib.DFK_GRAM_AUTO, "fp32": _lib.DFK_GRAM_FP32, "tf32x3": _lib.DFK_GRAM_TF32X3}[mode]
+        check(self._hd.h, lib().dfk_sfm_set_gram_mode(self._hd.h, m))
+
+    def SetEvalThreadsBlocks(self, threads: int, blocks: int):
+        self.params_.eval_threads, self.params_.eval_blocks = threads, blocks
+        cp = self.params_.to_c()
+        check(self._hd.h, lib().dfk_sfm_set_params(self._hd.h, C.byref(cp)))
+
+    def SetStepThreadsBlocks(self, threads: int, blocks: int):
+        self.params_.step_threads, self.params_.step_blocks = threads, blocks
+        cp = self.params_.to_c()
+        check(self._hd.h, lib().dfk_sfm_set_params(self._hd.h, C.byref(cp)))
+
+    def RunStep(self, pose0, pose1, code0, cam, img0, img1, dpt0, std0, valid0, prx0_jac, grad1) -> JTJJrReductionItem:
+        """cu_sfmaligner.h:76-86.  Synchronous, result by value."""
+        self._hd.use_torch_stream()
+        n = 12 + self.CS
+        JtJ = np.zeros(n * (n + 1) // 2, dtype=np.float32)
+        Jtr = np.zeros(n, dtype=np.float32)
+        res = C.c_float(0)
+        inl = C.c_uint64(0)
+        code = None if code0 is None else np.ascontiguousarray(code0, dtype=np.float32)
+        F = C.POINTER(C.c_float)
+        i0, i1, d0 = _image(img0), _image(img1), _image(dpt0)
+        s0 = None if std0 is None else _image(std0)
+        v0, jc, g1 = _image(valid0), _image(prx0_jac, self.CS), _image(grad1, 2)
+        cc = _cam(cam)
+        st = lib().dfk_sfm_run_step(self._hd.h, _pose(pose0), _pose(pose1),
+                                    None if code is None else code.ctypes.data_as(F), self.CS, C.byref(cc),
+                                    C.byref(i0), C.byref(i1), C.byref(d0), None if s0 is None else C.byref(s0),
+                                    C.byref(v0), C.byref(jc), C.byref(g1),
+                                    JtJ.ctypes.data_as(F), Jtr.ctypes.data_as(F), C.byref(res), C.byref(inl))
+        check(self._hd.h, st)
+        return JTJJrReductionItem(JtJ, Jtr, float(res.value), int(inl.value))
+
+    def EvaluateError(self, pose0, pose1, cam, img0, img1, dpt0, std0, grad1) -> CorrespondenceReductionItem:
+        """cu_sfmaligner.h:67-74."""
+        self._hd.use_torch_stream()
+        res = C.c_float(0)
+        inl = C.c_uint64(0)
+        i0, i1, d0 = _image(img0), _image(img1), _image(dpt0)
+        cc = _cam(cam)
+        st = lib().dfk_sfm_evaluate_error(self._hd.h, _pose(pose0), _pose(pose1), C.byref(cc), C.byref(i0),
+                                          C.byref(i1), C.byref(d0), None, None, C.byref(res), C.byref(inl))
+        check(self._hd.h, st)
+        return CorrespondenceReductionItem(float(res.value), int(inl.value))
+
+    # ---- batched extension (one persistent launch for many (pair, level) items) -----------------
+    def make_work_items(self, items: Sequence[dict]):
+        """items: dicts with pose0, pose1, cam, img0, img1, dpt0, valid0, prx0_jac, grad1."""
+        arr = (DfkSfmWorkItem * len(items))()
+        for k, it in enumerate(items):
+            w = arr[k]
+            w.pose0 = _pose(it["pose0"])
+            w.pose1 = _pose(it["pose1"])
+            w.cam = _cam(it["cam"])
+            w.img0, w.img1, w.dpt0 = _image(it["img0"]), _image(it["img1"]), _image(it["dpt0"])
+            w.valid0, w.prx0_jac, w.grad1 = _image(it["valid0"]), _image(it["prx0_jac"], self.CS), _image(it["grad1"], 2)
+        return arr
+
+    def RunStepBatch(self, work_items, records: torch.Tensor | None = None) -> torch.Tensor:
+        """Asynchronous: returns a device tensor [n, DFK_SFM_RECORD_FLOATS(CS)] on torch's current stream."""
+        self._hd.use_torch_stream()
+        n = len(work_items)
+        rec = _lib.record_floats(self.CS)
+        if records is None:
+            records = torch.empty((n, rec), dtype=torch.float32, device=f"cuda:{self._hd.device}")
+        assert records.is_contiguous() and records.numel() >= n * rec
+        st = lib().dfk_sfm_run_step_batch(self._hd.h, work_items, n, self.CS, C.c_void_p(records.data_ptr()))
+        check(self._hd.h, st)
+        return records
+
+    def unpack(self, records: torch.Tensor):
+        r = records.detach().cpu().numpy()
+        return [JTJJrReductionItem.from_record(r[i], self.CS) for i in range(r.shape[0])]
+
+
+# ------------------------------------------------------------------------------------------- SE3Aligner
+class SE3Aligner:
+    """df::SE3Aligner<float> (sources/cuda/cu_se3aligner.h:38-86)."""
+
+    def __init__(self, device=None):
+        self._hd = _Handle(device)
+        self._hd.use_torch_stream()
+        self.huber_delta_ = 0.1
+
+    def SetHuberDelta(self, val: float):
+        self.huber_delta_ = float(val)
+        check(self._hd.h, lib().dfk_se3_set_huber_delta(self._hd.h, C.c_float(val)))
+
+    def RunStep(self, se3, cam, img0, img1, dpt0, grad1) -> JTJJrReductionItem:
+        self._hd.use_torch_stream()
+        JtJ = np.zeros(21, dtype=np.float32)
+        Jtr = np.zeros(6, dtype=np.float32)
+        res = C.c_float(0)
+        inl = C.c_uint64(0)
+        F = C.POINTER(C.c_float)
+        i0, i1, d0, g1 = _image(img0), _image(img1), _image(dpt0), _image(grad1, 2)
+        cc = _cam(cam)
+        st = lib().dfk_se3_run_step(self._hd.h, _pose(se3), C.byref(cc), C.byref(i0), C.byref(i1), C.byref(d0),
+                                    C.byref(g1), JtJ.ctypes.data_as(F), Jtr.ctypes.data_as(F), C.byref(res),
+                                    C.byref(inl))
+        check(self._hd.h, st)
+        return JTJJrReductionItem(JtJ, Jtr, float(res.value), int(inl.value))
+
+    def Warp(self, se3, cam, img0, img1, dpt0, img2) -> CorrespondenceReductionItem:
+        self._hd.use_torch_stream()
+        res = C.c_float(0)
+        inl = C.c_uint64(0)
+        i0, i1, d0, i2 = _image(img0), _image(img1), _image(dpt0), _image(img2)
+        cc = _cam(cam)
+        st = lib().dfk_se3_warp(self._hd.h, _pose(se3), C.byref(cc), C.byref(i0), C.byref(i1), C.byref(d0),
+                                C.byref(i2), C.byref(res), C.byref(inl))
+        check(self._hd.h, st)
+        return CorrespondenceReductionItem(float(res.value), int(inl.value))
+
+
+# ------------------------------------------------------------------------------------------- free functions
+_default_handle = {}
+
+
+def _free_handle(device=None) -> _Handle:
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev not in _default_handle:
+        _default_handle[dev] = _Handle(dev)
+    hd = _default_handle[dev]
+    hd.use_torch_stream()
+    return hd
+
+
+def UpdateDepth(code, prx_orig, prx_jac, avg_dpt, dpt_out):
+    """df::UpdateDepth (cu_image_proc.cpp:266-277): dpt = avg/(prx_orig + prx_jac.code) - avg."""
+    hd = _free_handle(dpt_out.device)
+    code = np.ascontiguousarray(code, dtype=np.float32)
+    cs = int(code.shape[0])
+    p, j, d = _image(prx_orig), _image(prx_jac, cs), _image(dpt_out)
+    st = lib().dfk_update_depth(hd.h, code.ctypes.data_as(C.POINTER(C.c_float)), cs, C.byref(p), C.byref(j),
+                                C.c_float(avg_dpt), C.byref(d))
+    check(hd.h, st)
+
+
+def SobelGradients(img, grad):
+    """df::SobelGradients (cu_image_proc.cpp:95-113)."""
+    hd = _free_handle(img.device)
+    i, g = _image(img), _image(grad, 2)
+    check(hd.h, lib().dfk_sobel_gradients(hd.h, C.byref(i), C.byref(g)))
+
+
+def GaussianBlurDown(inp, out):
+    """df::GaussianBlurDown (cu_image_proc.cpp:166-184)."""
+    hd = _free_handle(inp.device)
+    i, o = _image(inp), _image(out)
+    check(hd.h, lib().dfk_gaussian_blur_down(hd.h, C.byref(i), C.byref(o)))
+
+
+def SquaredError(buf1, buf2) -> float:
+    """df::SquaredError (cu_image_proc.cpp:208-242)."""
+    hd = _free_handle(buf1.device)
+    a, b = _image(buf1), _image(buf2)
+    out = C.c_float(0)
+    check(hd.h, lib().dfk_squared_error(hd.h, C.byref(a), C.byref(b), C.byref(out)))
+    return float(out.value)

@@ -1,0 +1,645 @@
+// dfk_api.cu -- C ABI of libdfk.so (see include/dfk.h): argument validation, host-side SE3
+// algebra (relative pose + Jacobians, as the reference does on the host in
+// cu_sfmaligner.cpp:164-166), launch planning, scratch ownership, error reporting.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "dfk.h"
+#include "dfk_internal.h"
+
+using namespace dfk;
+
+struct DfkContext {
+  int device = 0;
+  int num_sms = 1;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  DfkSfmAlignerParams params;
+  DfkGramMode gram_mode = DFK_GRAM_AUTO;
+  float se3_huber_delta = 0.1f;  // cu_se3aligner.h:85
+
+  float* simple_scratch = nullptr;   // kSimpleScratchFloats
+  unsigned int* counter = nullptr;   // 1 (self-resetting ticket)
+  float* out_dev = nullptr;          // 32 floats
+  float* out_host = nullptr;         // pinned, 32 floats
+  float* code_dev = nullptr;         // 256 floats
+
+  SfmItemDev* items_dev = nullptr;
+  size_t items_cap = 0;
+  float* partials_dev = nullptr;
+  size_t partials_cap = 0;  // floats
+  float* records_dev = nullptr;
+  size_t records_cap = 0;  // floats
+  float* records_host = nullptr;  // pinned
+  size_t records_host_cap = 0;
+  std::vector<SfmItemDev> items_host;
+};
+
+namespace {
+
+DfkStatus fail(DfkHandle h, DfkStatus s, const std::string& msg)
+{
+  if (h) h->err = msg;
+  return s;
+}
+
+DfkStatus cuda_fail(DfkHandle h, cudaError_t e, const char* what)
+{
+  // message format of vc::CUDAException thrown from CudaCheckLastError (launch_utils.h:26-32)
+  std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();  // clear sticky-less errors
+  return fail(h, DFK_ERR_CUDA, m);
+}
+
+#define DFK_CUDA(h, call, what)                            \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) return cuda_fail(h, e__, what); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev)
+  {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard()
+  {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---------------------------------------------------------------------------- SE3 algebra (fp32)
+// Eigen QuaternionBase::_transformVector
+void quat_rotate(const float q[4], const float v[3], float out[3])
+{
+  float uv0 = q[1] * v[2] - q[2] * v[1];
+  float uv1 = q[2] * v[0] - q[0] * v[2];
+  float uv2 = q[0] * v[1] - q[1] * v[0];
+  uv0 += uv0; uv1 += uv1; uv2 += uv2;
+  out[0] = (v[0] + q[3] * uv0) + (q[1] * uv2 - q[2] * uv1);
+  out[1] = (v[1] + q[3] * uv1) + (q[2] * uv0 - q[0] * uv2);
+  out[2] = (v[2] + q[3] * uv2) + (q[0] * uv1 - q[1] * uv0);
+}
+
+void quat_mul(const float a[4], const float b[4], float o[4])
+{
+  const float w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  const float x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  const float y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  const float z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+
+void quat_to_matrix(const float q[4], float R[9])
+{
+  const float tx = 2.f * q[0], ty = 2.f * q[1], tz = 2.f * q[2];
+  const float twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+  const float txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+  const float tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  R[0] = 1.f - (tyy + tzz); R[1] = txy - twz;         R[2] = txz + twy;
+  R[3] = txy + twz;         R[4] = 1.f - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;         R[7] = tyz + twx;         R[8] = 1.f - (txx + tyy);
+}
+
+// warping.h:98-137 RelativePose(pose_a, pose_b, jac_a, jac_b): pose_ab = a^-1 * b
+void relative_pose(const float a[7], const float b[7], float ab[7], float* jac_a, float* jac_b)
+{
+  const float qi[4] = {-a[0], -a[1], -a[2], a[3]};
+  const float nta[3] = {-a[4], -a[5], -a[6]};
+  float ti[3], tmp[3];
+  quat_rotate(qi, nta, ti);
+  quat_mul(qi, b, ab);
+  quat_rotate(qi, b + 4, tmp);
+  ab[4] = ti[0] + tmp[0]; ab[5] = ti[1] + tmp[1]; ab[6] = ti[2] + tmp[2];
+  if (!jac_a && !jac_b) return;
+  float Ra[9], RaT[9];
+  quat_to_matrix(a, Ra);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) RaT[i * 3 + j] = Ra[j * 3 + i];
+  if (jac_a) {
+    const float d[3] = {a[4] - b[4], a[5] - b[5], a[6] - b[6]};
+    float v[3];
+    for (int i = 0; i < 3; ++i) v[i] = RaT[i * 3 + 0] * d[0] + RaT[i * 3 + 1] * d[1] + RaT[i * 3 + 2] * d[2];
+    const float hat[9] = {0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0};
+    for (int i = 0; i < 36; ++i) jac_a[i] = 0.f;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        float s = 0.f;
+        for (int k = 0; k < 3; ++k) s += hat[i * 3 + k] * RaT[k * 3 + j];
+        jac_a[i * 6 + j] = -RaT[i * 3 + j];
+        jac_a[i * 6 + 3 + j] = -s;
+        jac_a[(3 + i) * 6 + 3 + j] = -RaT[i * 3 + j];
+      }
+  }
+  if (jac_b) {
+    for (int i = 0; i < 36; ++i) jac_b[i] = 0.f;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        jac_b[i * 6 + j] = RaT[i * 3 + j];
+        jac_b[(3 + i) * 6 + 3 + j] = RaT[i * 3 + j];
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------- validation helpers
+bool img_ok(const DfkImage* im, uint32_t w, uint32_t h, uint32_t floats_per_px)
+{
+  return im && im->ptr && im->width == w && im->height == h && (im->pitch_bytes % 4 == 0) &&
+         im->pitch_bytes >= (size_t)w * floats_per_px * 4;
+}
+
+View view_of(const DfkImage* im) { return View{static_cast<const float*>(im->ptr), (uint32_t)(im->pitch_bytes / 4)}; }
+
+bool aligned(const void* p, size_t a) { return reinterpret_cast<uintptr_t>(p) % a == 0; }
+
+PixelCam make_pixel_cam(const float pose[7], const DfkCamera* cam, int border, float min_dpt)
+{
+  PixelCam pc;
+  for (int i = 0; i < 4; ++i) pc.q[i] = pose[i];
+  for (int i = 0; i < 3; ++i) pc.t[i] = pose[4 + i];
+  pc.fx = cam->fx; pc.fy = cam->fy; pc.u0 = cam->u0; pc.v0 = cam->v0;
+  pc.border = (float)border;
+  pc.ulim = cam->width - (float)border;   // PixelValid: x < width_ - border (pinhole_camera_impl.h:107)
+  pc.vlim = cam->height - (float)border;
+  pc.min_dpt = min_dpt;
+  return pc;
+}
+
+uint32_t gcd_u32(uint32_t a, uint32_t b)
+{
+  while (b) {
+    const uint32_t t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+// stride for the in-item tile permutation: ~golden-ratio of the tile count, coprime with it
+uint32_t perm_multiplier(uint32_t n)
+{
+  if (n <= 2) return 1;
+  uint32_t m = (uint32_t)((double)n * 0.6180339887498949);
+  if (m < 1) m = 1;
+  while (gcd_u32(m, n) != 1) ++m;
+  return m % n == 0 ? 1 : m;
+}
+
+template <typename T>
+cudaError_t ensure(T** ptr, size_t* cap, size_t need)
+{
+  if (*cap >= need) return cudaSuccess;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *cap = 0;
+  size_t n = std::max(need, (*cap) * 2);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(ptr), n * sizeof(T));
+  if (e == cudaSuccess) *cap = n;
+  return e;
+}
+
+DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, SfmLaunchPlan* plan)
+{
+  const DfkDenseSfmParams& sp = h->params.sfmparams;
+  h->items_host.resize(n);
+  uint32_t tile_cursor = 0;
+  for (int i = 0; i < n; ++i) {
+    const DfkSfmWorkItem& w = items[i];
+    SfmItemDev& d = h->items_host[i];
+    const uint32_t W = w.img0.width, H = w.img0.height;
+    if (W == 0 || H == 0) return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] empty image");
+    if (!img_ok(&w.img0, W, H, 1) || !img_ok(&w.img1, W, H, 1) || !img_ok(&w.dpt0, W, H, 1) ||
+        !img_ok(&w.valid0, W, H, 1) || !img_ok(&w.prx0_jac, W, H, code_size) || !img_ok(&w.grad1, W, H, 2))
+      return fail(h, DFK_ERR_INVALID_ARG,
+                  "[SfmAligner::RunStep] inconsistent image views (size, pitch or null pointer) in work item " +
+                      std::to_string(i));
+    float p10[7];
+    relative_pose(w.pose1, w.pose0, p10, d.P1, d.P0);  // RelativePose(pose1, pose0, J_pose1, J_pose0)
+    for (int k = 0; k < 4; ++k) d.q[k] = p10[k];
+    for (int k = 0; k < 3; ++k) d.t[k] = p10[4 + k];
+    quat_to_matrix(p10, d.R);
+    d.fx = w.cam.fx; d.fy = w.cam.fy; d.u0 = w.cam.u0; d.v0 = w.cam.v0;
+    d.border = (float)sp.valid_border;
+    d.ulim = w.cam.width - (float)sp.valid_border;
+    d.vlim = w.cam.height - (float)sp.valid_border;
+    d.min_dpt = sp.min_dpt; d.avg_dpt = sp.avg_dpt; d.huber_delta = sp.huber_delta;
+    d.img0 = (const float*)w.img0.ptr; d.img1 = (const float*)w.img1.ptr; d.dpt0 = (const float*)w.dpt0.ptr;
+    d.valid0 = (float*)w.valid0.ptr; d.jac = (const float*)w.prx0_jac.ptr; d.grad1 = (const float*)w.grad1.ptr;
+    d.img0_pitch = (uint32_t)(w.img0.pitch_bytes / 4); d.img1_pitch = (uint32_t)(w.img1.pitch_bytes / 4);
+    d.dpt0_pitch = (uint32_t)(w.dpt0.pitch_bytes / 4); d.valid0_pitch = (uint32_t)(w.valid0.pitch_bytes / 4);
+    d.jac_pitch = (uint32_t)(w.prx0_jac.pitch_bytes / 4); d.grad1_pitch = (uint32_t)(w.grad1.pitch_bytes / 4);
+    d.width = W; d.height = H; d.num_pixels = W * H;
+    d.num_tiles = (d.num_pixels + kTilePixels - 1) / kTilePixels;
+    d.tile_begin = tile_cursor;
+    tile_cursor += d.num_tiles;
+    d.perm_mul = perm_multiplier(d.num_tiles);
+    d.flags = 0;
+    const bool bulk = (W % 4 == 0) && aligned(d.img0, 16) && aligned(d.dpt0, 16) && aligned(d.jac, 16) &&
+                      (d.img0_pitch % 4 == 0) && (d.dpt0_pitch % 4 == 0) && (d.jac_pitch % 4 == 0) &&
+                      (code_size % 4 == 0);
+    if (bulk) d.flags |= ITEM_FLAG_BULK;
+    if (aligned(d.grad1, 8) && d.grad1_pitch % 2 == 0) d.flags |= ITEM_FLAG_GRAD_ALIGNED;
+  }
+  const int T = (int)tile_cursor;
+  int G = std::min(h->num_sms, T);
+  if (G < 1) G = 1;
+  plan->num_items = n;
+  plan->num_tiles = T;
+  plan->num_ctas = G;
+  // which CTAs touch which item (CTA c owns global tiles [c*T/G, (c+1)*T/G))
+  uint32_t partial_cursor = 0;
+  int c = 0;
+  int max_per_item = 0;
+  for (int i = 0; i < n; ++i) {
+    SfmItemDev& d = h->items_host[i];
+    const long long tb = d.tile_begin, te = tb + d.num_tiles;
+    while ((long long)(c + 1) * T / G <= tb) ++c;  // first CTA whose range ends after tb
+    int first = c, last = c;
+    while ((long long)(last + 1) * T / G < te) ++last;
+    d.first_cta = (uint32_t)first;
+    d.num_ctas = (uint32_t)(last - first + 1);
+    d.partial_begin = partial_cursor;
+    partial_cursor += d.num_ctas;
+    max_per_item = std::max(max_per_item, (int)d.num_ctas);
+  }
+  plan->num_partials = (int)partial_cursor;
+  plan->max_ctas_per_item = max_per_item;
+  return DFK_OK;
+}
+
+DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, float* records_dev)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!items || n <= 0 || !records_dev) return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] null/empty batch");
+  if (!sfm_fp32_supported(code_size))
+    return fail(h, DFK_ERR_UNSUPPORTED,
+                "[SfmAligner::RunStep] no kernel instantiated for code size " + std::to_string(code_size));
+  if (h->gram_mode == DFK_GRAM_TF32X3)
+    return fail(h, DFK_ERR_UNSUPPORTED, "[SfmAligner::RunStep] tensor-core Gram path not available in this build");
+  DeviceGuard guard(h->device);
+  SfmLaunchPlan plan;
+  DfkStatus st = build_items(h, items, n, code_size, &plan);
+  if (st != DFK_OK) return st;
+  DFK_CUDA(h, ensure(&h->items_dev, &h->items_cap, (size_t)n), "[SfmAligner::RunStep] scratch allocation failed");
+  DFK_CUDA(h, ensure(&h->partials_dev, &h->partials_cap, (size_t)plan.num_partials * sfm_partial_floats(code_size)),
+           "[SfmAligner::RunStep] scratch allocation failed");
+  DFK_CUDA(h, cudaMemcpyAsync(h->items_dev, h->items_host.data(), sizeof(SfmItemDev) * n, cudaMemcpyHostToDevice,
+                              h->stream),
+           "[SfmAligner::RunStep] work list upload failed");
+  DFK_CUDA(h, launch_sfm_fp32(code_size, h->items_dev, plan, h->partials_dev, records_dev, h->stream),
+           "[SfmAligner::RunStep] kernel launch failed");
+  return DFK_OK;
+}
+
+}  // namespace
+
+// ================================================================================== C ABI
+extern "C" {
+
+int dfk_version(void) { return DFK_VERSION; }
+
+const char* dfk_status_string(DfkStatus s)
+{
+  switch (s) {
+    case DFK_OK: return "ok";
+    case DFK_ERR_INVALID_ARG: return "invalid argument";
+    case DFK_ERR_CUDA: return "CUDA error";
+    case DFK_ERR_UNSUPPORTED: return "unsupported";
+    case DFK_ERR_NOMEM: return "out of memory";
+  }
+  return "unknown";
+}
+
+int dfk_sfm_supports_code_size(int code_size) { return sfm_fp32_supported(code_size) ? 1 : 0; }
+
+DfkStatus dfk_create(int device, DfkHandle* out)
+{
+  if (!out) return DFK_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return DFK_ERR_CUDA;
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) return DFK_ERR_CUDA;
+  }
+  if (device >= count) return DFK_ERR_INVALID_ARG;
+  DfkContext* h = new (std::nothrow) DfkContext();
+  if (!h) return DFK_ERR_NOMEM;
+  h->device = device;
+  h->params.sfmparams = DfkDenseSfmParams{0.1f, 1000.f, 2.0f, 0.0f, 2};
+  h->params.step_threads = 32; h->params.step_blocks = 11; h->params.eval_threads = 224; h->params.eval_blocks = 66;
+  DeviceGuard guard(device);
+  bool ok = true;
+  ok = ok && cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  h->stream = h->own_stream;
+  ok = ok && cudaMalloc((void**)&h->simple_scratch, sizeof(float) * kSimpleScratchFloats) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->counter, sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->out_dev, sizeof(float) * 32) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&h->code_dev, sizeof(float) * 256) == cudaSuccess;
+  ok = ok && cudaMallocHost((void**)&h->out_host, sizeof(float) * 32) == cudaSuccess;
+  ok = ok && cudaMemset(h->counter, 0, sizeof(unsigned int)) == cudaSuccess;
+  if (!ok) {
+    dfk_destroy(h);
+    return DFK_ERR_CUDA;
+  }
+  *out = h;
+  return DFK_OK;
+}
+
+DfkStatus dfk_destroy(DfkHandle h)
+{
+  if (!h) return DFK_OK;
+  DeviceGuard guard(h->device);
+  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+  cudaFree(h->simple_scratch); cudaFree(h->counter); cudaFree(h->out_dev); cudaFree(h->code_dev);
+  cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev);
+  if (h->out_host) cudaFreeHost(h->out_host);
+  if (h->records_host) cudaFreeHost(h->records_host);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return DFK_OK;
+}
+
+DfkStatus dfk_set_stream(DfkHandle h, void* cuda_stream)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return DFK_OK;
+}
+
+void* dfk_get_stream(DfkHandle h) { return h ? h->stream : nullptr; }
+
+DfkStatus dfk_synchronize(DfkHandle h)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  DFK_CUDA(h, cudaStreamSynchronize(h->stream), "stream synchronize failed");
+  return DFK_OK;
+}
+
+const char* dfk_last_error(DfkHandle h) { return h ? h->err.c_str() : "null handle"; }
+
+DfkStatus dfk_sfm_set_params(DfkHandle h, const DfkSfmAlignerParams* p)
+{
+  if (!h || !p) return DFK_ERR_INVALID_ARG;
+  // CHECK_EQ(threads % 32, 0), CHECK_LE(blocks, max_blocks) (cu_sfmaligner.cpp:187-203)
+  if (p->step_threads % 32 != 0 || p->eval_threads % 32 != 0)
+    return fail(h, DFK_ERR_INVALID_ARG, "threads must be a multiple of 32!");
+  if (p->step_blocks > 1024 || p->eval_blocks > 1024) return fail(h, DFK_ERR_INVALID_ARG, "blocks must be less than 1024");
+  if (p->sfmparams.valid_border < 1)
+    return fail(h, DFK_ERR_INVALID_ARG, "valid_border must be >= 1 (bilinear sampling reads ix+1, iy+1)");
+  h->params = *p;
+  return DFK_OK;
+}
+
+DfkStatus dfk_sfm_get_params(DfkHandle h, DfkSfmAlignerParams* p)
+{
+  if (!h || !p) return DFK_ERR_INVALID_ARG;
+  *p = h->params;
+  return DFK_OK;
+}
+
+DfkStatus dfk_sfm_set_gram_mode(DfkHandle h, DfkGramMode m)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (m != DFK_GRAM_AUTO && m != DFK_GRAM_FP32 && m != DFK_GRAM_TF32X3)
+    return fail(h, DFK_ERR_INVALID_ARG, "unknown gram mode");
+  h->gram_mode = m;
+  return DFK_OK;
+}
+
+DfkStatus dfk_se3_set_huber_delta(DfkHandle h, float v)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  h->se3_huber_delta = v;
+  return DFK_OK;
+}
+
+DfkStatus dfk_sfm_run_step_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, float* records_dev)
+{
+  return run_batch(h, items, n, code_size, records_dev);
+}
+
+DfkStatus dfk_sfm_run_step_batch_host(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size,
+                                      float* records_host)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!records_host || n <= 0) return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] null/empty batch");
+  DeviceGuard guard(h->device);
+  const size_t rec = (size_t)DFK_SFM_RECORD_FLOATS(code_size);
+  DFK_CUDA(h, ensure(&h->records_dev, &h->records_cap, rec * n), "[SfmAligner::RunStep] scratch allocation failed");
+  if (h->records_host_cap < rec * n) {
+    if (h->records_host) cudaFreeHost(h->records_host);
+    h->records_host = nullptr;
+    h->records_host_cap = 0;
+    DFK_CUDA(h, cudaMallocHost((void**)&h->records_host, rec * n * sizeof(float)),
+             "[SfmAligner::RunStep] pinned allocation failed");
+    h->records_host_cap = rec * n;
+  }
+  DfkStatus st = run_batch(h, items, n, code_size, h->records_dev);
+  if (st != DFK_OK) return st;
+  DFK_CUDA(h, cudaMemcpyAsync(h->records_host, h->records_dev, rec * n * sizeof(float), cudaMemcpyDeviceToHost,
+                              h->stream),
+           "[SfmAligner::RunStep] result download failed");
+  DFK_CUDA(h, cudaStreamSynchronize(h->stream), "[SfmAligner::RunStep] kernel launch failed");
+  memcpy(records_host, h->records_host, rec * n * sizeof(float));
+  return DFK_OK;
+}
+
+DfkStatus dfk_sfm_run_step(DfkHandle h, const float pose0[7], const float pose1[7], const float* /*code0*/,
+                           int code_size, const DfkCamera* cam, const DfkImage* img0, const DfkImage* img1,
+                           const DfkImage* dpt0, const DfkImage* /*std0*/, const DfkImage* valid0,
+                           const DfkImage* prx0_jac, const DfkImage* grad1, float* JtJ, float* Jtr, float* residual,
+                           uint64_t* inliers)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!pose0 || !pose1 || !cam || !img0 || !img1 || !dpt0 || !valid0 || !prx0_jac || !grad1 || !JtJ || !Jtr ||
+      !residual || !inliers)
+    return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] null argument");
+  DfkSfmWorkItem w;
+  memcpy(w.pose0, pose0, sizeof(w.pose0));
+  memcpy(w.pose1, pose1, sizeof(w.pose1));
+  w.cam = *cam;
+  w.img0 = *img0; w.img1 = *img1; w.dpt0 = *dpt0; w.valid0 = *valid0; w.prx0_jac = *prx0_jac; w.grad1 = *grad1;
+  const int NP = 12 + code_size;
+  const int NH = NP * (NP + 1) / 2;
+  std::vector<float> rec((size_t)DFK_SFM_RECORD_FLOATS(code_size));
+  DfkStatus st = dfk_sfm_run_step_batch_host(h, &w, 1, code_size, rec.data());
+  if (st != DFK_OK) return st;
+  memcpy(JtJ, rec.data(), sizeof(float) * NH);
+  memcpy(Jtr, rec.data() + NH, sizeof(float) * NP);
+  *residual = rec[NH + NP];
+  uint32_t bits;
+  memcpy(&bits, &rec[NH + NP + 1], 4);
+  *inliers = bits;
+  return DFK_OK;
+}
+
+static DfkStatus fetch_out(DfkHandle h, int nfloats, const char* what)
+{
+  DFK_CUDA(h, cudaMemcpyAsync(h->out_host, h->out_dev, sizeof(float) * nfloats, cudaMemcpyDeviceToHost, h->stream),
+           what);
+  DFK_CUDA(h, cudaStreamSynchronize(h->stream), what);
+  return DFK_OK;
+}
+
+DfkStatus dfk_sfm_evaluate_error(DfkHandle h, const float pose0[7], const float pose1[7], const DfkCamera* cam,
+                                 const DfkImage* img0, const DfkImage* img1, const DfkImage* dpt0,
+                                 const DfkImage* /*std0*/, const DfkImage* /*grad1*/, float* residual,
+                                 uint64_t* inliers)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!pose0 || !pose1 || !cam || !img0 || !img1 || !dpt0 || !residual || !inliers)
+    return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::EvaluateError] null argument");
+  const uint32_t W = img0->width, H = img0->height;
+  if (W == 0 || H == 0 || !img_ok(img0, W, H, 1) || !img_ok(img1, W, H, 1) || !img_ok(dpt0, W, H, 1))
+    return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::EvaluateError] inconsistent image views");
+  DeviceGuard guard(h->device);
+  float p10[7];
+  relative_pose(pose1, pose0, p10, nullptr, nullptr);  // cu_sfmaligner.cpp:131
+  // DenseSfm_EvaluateError uses FindCorrespondence defaults: border 1, min_dpt 0 (dense_sfm.h:91)
+  const PixelCam pc = make_pixel_cam(p10, cam, 1, 0.0f);
+  DFK_CUDA(h, launch_eval_error(pc, h->params.sfmparams.huber_delta, (int)W, (int)H, view_of(img0), view_of(img1),
+                                view_of(dpt0), h->simple_scratch, h->counter, h->out_dev, h->stream),
+           "[SfmAligner::EvaluateError] kernel launch failed");
+  DfkStatus st = fetch_out(h, 2, "[SfmAligner::EvaluateError] kernel launch failed");
+  if (st != DFK_OK) return st;
+  *residual = h->out_host[0];
+  uint32_t bits;
+  memcpy(&bits, &h->out_host[1], 4);
+  *inliers = bits;
+  return DFK_OK;
+}
+
+DfkStatus dfk_se3_run_step(DfkHandle h, const float se3[7], const DfkCamera* cam, const DfkImage* img0,
+                           const DfkImage* img1, const DfkImage* dpt0, const DfkImage* grad1, float* JtJ, float* Jtr,
+                           float* residual, uint64_t* inliers)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!se3 || !cam || !img0 || !img1 || !dpt0 || !grad1 || !JtJ || !Jtr || !residual || !inliers)
+    return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::RunStep] null argument");
+  const uint32_t W = img0->width, H = img0->height;
+  if (W == 0 || H == 0 || !img_ok(img0, W, H, 1) || !img_ok(img1, W, H, 1) || !img_ok(dpt0, W, H, 1) ||
+      !img_ok(grad1, W, H, 2))
+    return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::RunStep] inconsistent image views");
+  DeviceGuard guard(h->device);
+  const PixelCam pc = make_pixel_cam(se3, cam, 1, 0.0f);  // lucas_kanade_se3.h:52 defaults
+  const View g = view_of(grad1);
+  const bool galigned = aligned(g.ptr, 8) && g.pitch % 2 == 0;
+  DFK_CUDA(h, launch_se3_step(pc, h->se3_huber_delta, (int)W, (int)H, view_of(img0), view_of(img1), view_of(dpt0), g,
+                              galigned, h->simple_scratch, h->counter, h->out_dev, h->stream),
+           "[SE3Aligner::RunStep] Kernel launch failed");
+  DfkStatus st = fetch_out(h, 29, "[SE3Aligner::RunStep] Kernel launch failed");
+  if (st != DFK_OK) return st;
+  memcpy(JtJ, h->out_host, sizeof(float) * 21);
+  memcpy(Jtr, h->out_host + 21, sizeof(float) * 6);
+  *residual = h->out_host[27];
+  uint32_t bits;
+  memcpy(&bits, &h->out_host[28], 4);
+  *inliers = bits;
+  return DFK_OK;
+}
+
+DfkStatus dfk_se3_warp(DfkHandle h, const float se3[7], const DfkCamera* cam, const DfkImage* img0,
+                       const DfkImage* img1, const DfkImage* dpt0, const DfkImage* img2, float* residual,
+                       uint64_t* inliers)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!se3 || !cam || !img0 || !img1 || !dpt0 || !img2 || !residual || !inliers)
+    return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::Warp] null argument");
+  const uint32_t W = img0->width, H = img0->height;
+  if (W == 0 || H == 0 || !img_ok(img0, W, H, 1) || !img_ok(img1, W, H, 1) || !img_ok(dpt0, W, H, 1) ||
+      !img_ok(img2, W, H, 1))
+    return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::Warp] inconsistent image views");
+  DeviceGuard guard(h->device);
+  // depth <= 0 -> skip ; PixelValid(pix1, 1) (cu_se3aligner.cpp:89-97)
+  const PixelCam pc = make_pixel_cam(se3, cam, 1, 0.0f);
+  DFK_CUDA(h, launch_warp(pc, (int)W, (int)H, view_of(img0), view_of(img1), view_of(dpt0), (float*)img2->ptr,
+                          (uint32_t)(img2->pitch_bytes / 4), h->simple_scratch, h->counter, h->out_dev, h->stream),
+           "[SE3Aligner::Warp] Kernel launch failed (kernel_warp_calculate)");
+  DfkStatus st = fetch_out(h, 2, "[SE3Aligner::Warp] Kernel launch failed (kernel_finalize_reduction)");
+  if (st != DFK_OK) return st;
+  *residual = h->out_host[0];
+  uint32_t bits;
+  memcpy(&bits, &h->out_host[1], 4);
+  *inliers = bits;
+  return DFK_OK;
+}
+
+DfkStatus dfk_update_depth(DfkHandle h, const float* code, int code_size, const DfkImage* prx_orig,
+                           const DfkImage* prx_jac, float avg_dpt, const DfkImage* dpt_out)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!code || !prx_orig || !prx_jac || !dpt_out) return fail(h, DFK_ERR_INVALID_ARG, "[UpdateDepth] null argument");
+  if (code_size < 1 || code_size > 256) return fail(h, DFK_ERR_UNSUPPORTED, "[UpdateDepth] code size out of range");
+  const uint32_t W = dpt_out->width, H = dpt_out->height;
+  if (W == 0 || H == 0 || !img_ok(prx_orig, W, H, 1) || !img_ok(prx_jac, W, H, code_size) || !img_ok(dpt_out, W, H, 1))
+    return fail(h, DFK_ERR_INVALID_ARG, "[UpdateDepth] inconsistent image views");
+  DeviceGuard guard(h->device);
+  DFK_CUDA(h, cudaMemcpyAsync(h->code_dev, code, sizeof(float) * code_size, cudaMemcpyHostToDevice, h->stream),
+           "[UpdateDepth] code upload failed");
+  DFK_CUDA(h, launch_update_depth(h->code_dev, code_size, (int)W, (int)H, view_of(prx_orig), view_of(prx_jac),
+                                  avg_dpt, (float*)dpt_out->ptr, (uint32_t)(dpt_out->pitch_bytes / 4), h->stream),
+           "[UpdateDepth] kernel launch failed");
+  return DFK_OK;
+}
+
+DfkStatus dfk_sobel_gradients(DfkHandle h, const DfkImage* img, const DfkImage* grad)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!img || !grad) return fail(h, DFK_ERR_INVALID_ARG, "[SobelGradients] null argument");
+  const uint32_t W = img->width, H = img->height;
+  if (W == 0 || H == 0 || !img_ok(img, W, H, 1) || !img_ok(grad, W, H, 2))
+    return fail(h, DFK_ERR_INVALID_ARG, "[SobelGradients] inconsistent image views");
+  DeviceGuard guard(h->device);
+  DFK_CUDA(h, launch_sobel((int)W, (int)H, view_of(img), (float*)grad->ptr, (uint32_t)(grad->pitch_bytes / 4),
+                           h->stream),
+           "Kernel launch failed (kernel_sobel_gradients)");
+  return DFK_OK;
+}
+
+DfkStatus dfk_gaussian_blur_down(DfkHandle h, const DfkImage* in, const DfkImage* out)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!in || !out) return fail(h, DFK_ERR_INVALID_ARG, "[GaussianBlurDown] null argument");
+  if (in->width == 0 || in->height == 0 || out->width == 0 || out->height == 0 ||
+      !img_ok(in, in->width, in->height, 1) || !img_ok(out, out->width, out->height, 1))
+    return fail(h, DFK_ERR_INVALID_ARG, "[GaussianBlurDown] inconsistent image views");
+  DeviceGuard guard(h->device);
+  DFK_CUDA(h, launch_blur_down((int)in->width, (int)in->height, view_of(in), (int)out->width, (int)out->height,
+                               (float*)out->ptr, (uint32_t)(out->pitch_bytes / 4), h->stream),
+           "Kernel launch failed (kernel_gaussian_blur_down)");
+  return DFK_OK;
+}
+
+DfkStatus dfk_squared_error(DfkHandle h, const DfkImage* a, const DfkImage* b, float* out)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!a || !b || !out) return fail(h, DFK_ERR_INVALID_ARG, "[SquaredError] null argument");
+  const uint32_t W = a->width, H = a->height;
+  if (W == 0 || H == 0 || !img_ok(a, W, H, 1) || !img_ok(b, W, H, 1))
+    return fail(h, DFK_ERR_INVALID_ARG, "[SquaredError] inconsistent image views");
+  DeviceGuard guard(h->device);
+  DFK_CUDA(h, launch_squared_error((int)W, (int)H, view_of(a), view_of(b), h->simple_scratch, h->counter, h->out_dev,
+                                   h->stream),
+           "[SquaredError] kernel launch failed");
+  DfkStatus st = fetch_out(h, 1, "[SquaredError] kernel launch failed");
+  if (st != DFK_OK) return st;
+  *out = h->out_host[0];
+  return DFK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// dfk_internal.h -- shared between the translation units of libdfk.so (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "dfk.h"
+
+namespace dfk {
+
+// ----------------------------------------------------------------------------------------------
+// Device-side description of one (keyframe, frame, level) evaluation.  Built on the host by
+// dfk_api.cu from a DfkSfmWorkItem: the relative pose and its two 6x6 Jacobians are host work in
+// the reference too (cu_sfmaligner.cpp:164-166).
+// ----------------------------------------------------------------------------------------------
+struct SfmItemDev {
+  // pose_10 = pose1^-1 * pose0 : quaternion (x,y,z,w), translation, and the same rotation as a
+  // row-major 3x3 (used only for derivative terms, never for the validity chain)
+  float q[4];
+  float t[3];
+  float R[9];
+  // camera (pinhole_camera.h:43) + validity window (pinhole_camera_impl.h:102-108)
+  float fx, fy, u0, v0;
+  float border;  // (float)valid_border
+  float ulim;    // width  - border  (float arithmetic as in the reference)
+  float vlim;    // height - border
+  float min_dpt, avg_dpt, huber_delta;
+  // buffers; pitches in floats
+  const float* img0;
+  const float* img1;
+  const float* dpt0;
+  float* valid0;
+  const float* jac;
+  const float* grad1;
+  uint32_t img0_pitch, img1_pitch, dpt0_pitch, valid0_pitch, jac_pitch, grad1_pitch;
+  uint32_t width, height;
+  uint32_t num_pixels;
+  // tiling
+  uint32_t tile_begin;  // first global tile index of this item
+  uint32_t num_tiles;
+  uint32_t perm_mul;    // tile k of the item is processed as (k * perm_mul) % num_tiles
+  // partial-sum bookkeeping: CTA c (first_cta <= c < first_cta+num_ctas) writes slot
+  // partial_begin + (c - first_cta)
+  uint32_t first_cta, num_ctas, partial_begin;
+  uint32_t flags;  // bit0: bulk-copy (TMA) eligible, bit1: grad1 rows are 8-byte aligned
+  // relative-pose Jacobians (warping.h:120-134), row-major 6x6; used by the finalize kernel
+  float P0[36];
+  float P1[36];
+};
+
+enum : uint32_t { ITEM_FLAG_BULK = 1u, ITEM_FLAG_GRAD_ALIGNED = 2u };
+
+// Geometry of the fp32 Gram kernel, shared by host planning code and the kernel.
+template <int C>
+struct SfmCfg {
+  static constexpr int NF = C + 7;               // features: code(C) | a(6) | r(1)
+  static constexpr int NFP = (NF + 7) & ~7;      // padded to 8
+  static constexpr int NB = NFP / 8;             // 8x8 blocks per side
+  static constexpr int NBLK = NB * (NB + 1) / 2;  // upper-triangular blocks
+  static constexpr int PARTIAL_FLOATS = NFP * NFP + 8;  // G (row major NFP x NFP) | inliers(u32) | pad
+};
+
+constexpr int kTilePixels = 256;
+
+struct SfmLaunchPlan {
+  int num_items = 0;
+  int num_tiles = 0;
+  int num_ctas = 0;
+  int num_partials = 0;
+  int max_ctas_per_item = 0;
+};
+
+// dfk_sfm_fp32.cu
+cudaError_t launch_sfm_fp32(int code_size, const SfmItemDev* items_dev, const SfmLaunchPlan& plan,
+                            float* partials_dev, float* records_dev, cudaStream_t stream);
+size_t sfm_partial_floats(int code_size);
+bool sfm_fp32_supported(int code_size);
+int sfm_max_ctas();  // grid size of the persistent kernel on the current device
+
+// dfk_simple.cu : single-pass reductions with a last-block finalize
+struct PixelCam {
+  float q[4], t[3];
+  float fx, fy, u0, v0, border, ulim, vlim, min_dpt;
+};
+struct View {
+  const float* ptr;
+  uint32_t pitch;  // floats
+};
+cudaError_t launch_se3_step(const PixelCam& pc, float huber_delta, int width, int height, View img0, View img1,
+                            View dpt0, View grad1, bool grad_aligned, float* scratch, unsigned int* counter,
+                            float* out_dev /*29 floats: 21 JtJ, 6 Jtr, res, inliers bits*/, cudaStream_t s);
+cudaError_t launch_eval_error(const PixelCam& pc, float huber_delta, int width, int height, View img0, View img1,
+                              View dpt0, float* scratch, unsigned int* counter, float* out_dev /*2*/, cudaStream_t s);
+cudaError_t launch_warp(const PixelCam& pc, int width, int height, View img0, View img1, View dpt0, float* img2,
+                        uint32_t img2_pitch, float* scratch, unsigned int* counter, float* out_dev /*2*/,
+                        cudaStream_t s);
+cudaError_t launch_update_depth(const float* code_dev, int code_size, int width, int height, View prx_orig, View jac,
+                                float avg_dpt, float* dpt, uint32_t dpt_pitch, cudaStream_t s);
+cudaError_t launch_sobel(int width, int height, View img, float* grad, uint32_t grad_pitch, cudaStream_t s);
+cudaError_t launch_blur_down(int in_w, int in_h, View in, int out_w, int out_h, float* out, uint32_t out_pitch,
+                             cudaStream_t s);
+cudaError_t launch_squared_error(int width, int height, View a, View b, float* scratch, unsigned int* counter,
+                                 float* out_dev, cudaStream_t s);
+constexpr int kSimpleMaxBlocks = 1024;
+constexpr int kSimpleScratchFloats = kSimpleMaxBlocks * 32;
+
+}  // namespace dfk

@@ -1,0 +1,607 @@
+// dfk_sfm_fp32.cu -- SfmAligner::RunStep hot path, fp32 CUDA-core Gram variant (sm_100a).
+//
+// Replaces kernel_step_calculate + DenseSfm + runReductions/finalizeReduction +
+// kernel_finalize_reduction of the reference (sources/cuda/cu_sfmaligner.cpp:40-70,
+// sources/common/algorithm/dense_sfm.h:133-201, sources/cuda/kernel_utils.h:51-69).
+//
+// Design (see DESIGN.md "fp32 Gram kernel"):
+//   * ONE persistent launch evaluates a whole list of (pair, level) items.  The pixel stream
+//     of every item is cut into tiles of 256 linear pixels; CTA c owns a contiguous range of
+//     the global tile sequence (static => bitwise reproducible results), tiles inside an item
+//     are visited in a strided order so that spatially clustered invalid regions balance out.
+//   * Per tile the TMA engine (cp.async.bulk, 1-D row segments) stages the code-Jacobian rows
+//     (C contiguous floats per pixel), img0 and dpt0 into a 3-deep shared-memory ring.
+//   * 4 "front-end" warps (one thread per pixel) run the exact-order validity chain, gather
+//     img1/grad1 bilinearly, form the reduced row  m = w*[ e*jc (C) | a (6) | diff (1) ]  and
+//     write it, compacted to valid pixels, K-major into a double-buffered tile M[feature][pixel].
+//   * NBLK "Gram" warps each own one 8x8 block of the upper triangle of G = sum m^T m
+//     ((7+C)^2, the (6+C) reduced system + gradient + energy of SURVEY Appendix A) with lanes
+//     striding over pixels; 64 register accumulators per thread, operands via conflict-free
+//     LDS.  Accumulators are reduce-scattered across lanes only when the CTA leaves an item.
+//   * A second, wide kernel sums the per-CTA partials in fixed order and expands the reduced
+//     system to the reference's (12+C) layout with the host-computed relative-pose Jacobians:
+//     JtJ = E^T G E,  E = [[P0,P1,0],[0,0,I]].
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dfk_async.cuh"
+#include "dfk_geom.cuh"
+#include "dfk_internal.h"
+
+namespace dfk {
+
+namespace {
+
+constexpr int kStages = 3;
+constexpr int kFeWarps = 4;
+constexpr int kFeThreads = kFeWarps * 32;
+constexpr int kPxPerFeThread = kTilePixels / kFeThreads;  // 2
+static_assert(kTilePixels % kFeThreads == 0, "tile must be a multiple of the front-end width");
+
+struct TileMeta {
+  int nvalid;
+  int item_changed;  // 1 if this tile starts a new item for this CTA
+  int slot;          // partial slot of the tile's item
+  int pad;
+};
+
+// per-item parameters the front-end needs, copied to shared memory when the CTA enters an item
+struct ItemSmem {
+  float q[4];
+  float t[3];
+  float R[9];
+  float fx, fy, u0, v0, border, ulim, vlim, min_dpt, avg_dpt, huber_delta;
+  const float* img0;
+  const float* img1;
+  const float* dpt0;
+  float* valid0;
+  const float* jac;
+  const float* grad1;
+  uint32_t img0_pitch, img1_pitch, dpt0_pitch, valid0_pitch, jac_pitch, grad1_pitch;
+  uint32_t width, height, num_pixels, tile_begin, num_tiles, perm_mul, flags, slot;
+};
+
+template <int C>
+struct Smem {
+  using Cfg = SfmCfg<C>;
+  alignas(128) float jc[kStages][kTilePixels * C];
+  alignas(16) float img0[kStages][kTilePixels];
+  alignas(16) float dpt0[kStages][kTilePixels];
+  alignas(16) float M[2][Cfg::NFP * kTilePixels];
+  alignas(8) uint64_t full_tma[kStages];
+  uint64_t m_full[2];
+  uint64_t m_empty[2];
+  TileMeta meta[2];
+  ItemSmem item;
+  int cnt[kPxPerFeThread * kFeWarps];  // valid counts per (round, warp)
+};
+
+// reduce-scatter of 64 per-lane accumulators: afterwards lane l holds the warp-wide sums of
+// entries 2l and 2l+1 in acc[0], acc[1].  62 shuffles; fixed order => deterministic.
+__device__ __forceinline__ void reduce_scatter64(float (&acc)[64], int lane)
+{
+#pragma unroll
+  for (int m = 16, n = 64; m >= 1; m >>= 1, n >>= 1) {
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? acc[i] : acc[i + n / 2];
+      const float keep = up ? acc[i + n / 2] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+}
+
+__device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, int tid, int nthreads, int cta)
+{
+  // field-wise copy by a few threads (small, once per item)
+  if (tid < 4) dst.q[tid] = src.q[tid];
+  if (tid < 3) dst.t[tid] = src.t[tid];
+  if (tid < 9) dst.R[tid] = src.R[tid];
+  if (tid == 32 % nthreads) {
+    dst.fx = src.fx; dst.fy = src.fy; dst.u0 = src.u0; dst.v0 = src.v0;
+    dst.border = src.border; dst.ulim = src.ulim; dst.vlim = src.vlim;
+    dst.min_dpt = src.min_dpt; dst.avg_dpt = src.avg_dpt; dst.huber_delta = src.huber_delta;
+  }
+  if (tid == 64 % nthreads) {
+    dst.img0 = src.img0; dst.img1 = src.img1; dst.dpt0 = src.dpt0; dst.valid0 = src.valid0;
+    dst.jac = src.jac; dst.grad1 = src.grad1;
+    dst.img0_pitch = src.img0_pitch; dst.img1_pitch = src.img1_pitch; dst.dpt0_pitch = src.dpt0_pitch;
+    dst.valid0_pitch = src.valid0_pitch; dst.jac_pitch = src.jac_pitch; dst.grad1_pitch = src.grad1_pitch;
+  }
+  if (tid == 96 % nthreads) {
+    dst.width = src.width; dst.height = src.height; dst.num_pixels = src.num_pixels;
+    dst.tile_begin = src.tile_begin; dst.num_tiles = src.num_tiles; dst.perm_mul = src.perm_mul;
+    dst.flags = src.flags;
+    dst.slot = src.partial_begin + (uint32_t)cta - src.first_cta;
+  }
+}
+
+// Issue the bulk copies of global tile g (item `it`) into ring stage `st`.  One thread.
+template <int C>
+__device__ __forceinline__ void issue_tile_loads(Smem<C>& sm, const SfmItemDev* __restrict__ items, int it, int g,
+                                                 int st)
+{
+  const SfmItemDev& I = items[it];
+  const uint32_t k = (uint32_t)g - I.tile_begin;
+  const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
+  const uint32_t p0 = tau * kTilePixels;
+  const uint32_t n = min((uint32_t)kTilePixels, I.num_pixels - p0);
+  const uint32_t W = I.width;
+  uint32_t y = p0 / W;
+  uint32_t x = p0 - y * W;
+  mbar_arrive_expect_tx(&sm.full_tma[st], n * (C + 2) * 4u);
+  uint32_t slot = 0;
+  while (slot < n) {
+    const uint32_t seg = min(W - x, n - slot);
+    bulk_g2s(&sm.jc[st][slot * C], I.jac + (size_t)y * I.jac_pitch + (size_t)x * C, seg * C * 4u, &sm.full_tma[st]);
+    bulk_g2s(&sm.img0[st][slot], I.img0 + (size_t)y * I.img0_pitch + x, seg * 4u, &sm.full_tma[st]);
+    bulk_g2s(&sm.dpt0[st][slot], I.dpt0 + (size_t)y * I.dpt0_pitch + x, seg * 4u, &sm.full_tma[st]);
+    slot += seg;
+    x = 0;
+    ++y;
+  }
+}
+
+// cooperative (non-TMA) staging for items whose buffers are not 16-byte friendly
+template <int C>
+__device__ __forceinline__ void coop_tile_loads(Smem<C>& sm, const ItemSmem& I, uint32_t p0, uint32_t n, int st,
+                                                int tid)
+{
+  const uint32_t W = I.width;
+  for (uint32_t s = tid; s < n; s += kFeThreads) {
+    const uint32_t p = p0 + s;
+    const uint32_t y = p / W, x = p - y * W;
+    sm.img0[st][s] = __ldg(I.img0 + (size_t)y * I.img0_pitch + x);
+    sm.dpt0[st][s] = __ldg(I.dpt0 + (size_t)y * I.dpt0_pitch + x);
+  }
+  for (uint32_t e = tid; e < n * C; e += kFeThreads) {
+    const uint32_t s = e / C, kk = e - s * C;
+    const uint32_t p = p0 + s;
+    const uint32_t y = p / W, x = p - y * W;
+    sm.jc[st][e] = __ldg(I.jac + (size_t)y * I.jac_pitch + (size_t)x * C + kk);
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__((kFeWarps + SfmCfg<C>::NBLK) * 32, 1)
+sfm_step_fp32_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_tiles, float* __restrict__ partials)
+{
+  using Cfg = SfmCfg<C>;
+  constexpr int NFP = Cfg::NFP;
+  constexpr int NB = Cfg::NB;
+  constexpr int NBLK = Cfg::NBLK;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem<C>& sm = *reinterpret_cast<Smem<C>*>(smem_raw);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int G = gridDim.x;
+  const int g_lo = (int)(((long long)cta * num_tiles) / G);
+  const int g_hi = (int)(((long long)(cta + 1) * num_tiles) / G);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&sm.full_tma[s], 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm.m_full[b], kFeThreads);
+      mbar_init(&sm.m_empty[b], NBLK);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (g_lo >= g_hi) return;
+
+  if (warp < kFeWarps) {
+    // ========================================================================= front-end
+    // item cursors: `it` for the tile being processed, `it_pf` for the prefetcher
+    int it = 0;
+    while (it + 1 < num_items && (uint32_t)g_lo >= items[it].tile_begin + items[it].num_tiles) ++it;
+    int it_pf = it;
+    uint32_t tma_phase_bits = 0;  // bit s = parity to wait for on stage s
+    int cur_item = -1;
+
+    // prologue: prefetch the first kStages tiles
+    if (tid == 0) {
+      for (int j = 0; j < kStages && g_lo + j < g_hi; ++j) {
+        const int g = g_lo + j;
+        while ((uint32_t)g >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
+        if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads<C>(sm, items, it_pf, g, j);
+      }
+    }
+
+    for (int g = g_lo, i = 0; g < g_hi; ++g, ++i) {
+      const int st = i % kStages;
+      const int buf = i & 1;
+      while ((uint32_t)g >= items[it].tile_begin + items[it].num_tiles) ++it;
+      const bool changed = (it != cur_item);
+      if (changed) {
+        named_bar_sync(1, kFeThreads);  // everyone finished reading the previous item's params
+        load_item(sm.item, items[it], tid, kFeThreads, cta);
+        cur_item = it;
+        named_bar_sync(1, kFeThreads);
+      }
+      const ItemSmem& I = sm.item;
+      const uint32_t k = (uint32_t)g - I.tile_begin;
+      const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
+      const uint32_t p0 = tau * kTilePixels;
+      const uint32_t n = min((uint32_t)kTilePixels, I.num_pixels - p0);
+      const bool bulk = (I.flags & ITEM_FLAG_BULK) != 0;
+      if (bulk) {
+        mbar_wait(&sm.full_tma[st], (tma_phase_bits >> st) & 1u);
+        tma_phase_bits ^= (1u << st);
+      } else {
+        coop_tile_loads<C>(sm, I, p0, n, st, tid);
+        named_bar_sync(1, kFeThreads);
+      }
+
+      // ---- geometry for this thread's pixels ------------------------------------------------
+      float feat[kPxPerFeThread][8];  // s, wa0..5, wr
+      bool ok[kPxPerFeThread];
+#pragma unroll
+      for (int r = 0; r < kPxPerFeThread; ++r) {
+        const uint32_t s = r * kFeThreads + tid;
+        ok[r] = false;
+        if (s < n) {
+          const uint32_t p = p0 + s;
+          const uint32_t y = p / I.width, x = p - y * I.width;
+          const float d = sm.dpt0[st][s];
+          const Warped w = warp_pixel((float)x, (float)y, d, I.q, I.t, I.fx, I.fy, I.u0, I.v0, I.border, I.ulim,
+                                      I.vlim, I.min_dpt);
+          if (w.valid) {
+            ok[r] = true;
+            I.valid0[(size_t)y * I.valid0_pitch + x] = 1.0f;  // dense_sfm.h:161
+            int ix, iy;
+            float fu, fv, gx, gy;
+            bilin_setup(w.u, w.v, ix, iy, fu, fv);
+            sample_grad(I.grad1, I.grad1_pitch, (I.flags & ITEM_FLAG_GRAD_ALIGNED) != 0, ix, iy, fu, fv, gx, gy);
+            const float i1 = sample_scalar(I.img1, I.img1_pitch, ix, iy, fu, fv);
+            float a[6], c00, c02, c11, c12;
+            pose_jacobian_row(w, I.fx, I.fy, gx, gy, a, c00, c02, c11, c12);
+            const float e = prx_jacobian(w, I.R, d, I.avg_dpt, gx, gy, c00, c02, c11, c12);
+            const float diff = sm.img0[st][s] - i1;
+            const float hw = huber_weight(diff, I.huber_delta);
+            feat[r][0] = hw * e;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) feat[r][1 + j] = hw * a[j];
+            feat[r][7] = hw * diff;
+          }
+        }
+      }
+
+      // ---- compaction: valid pixels first --------------------------------------------------
+      int rank[kPxPerFeThread];
+#pragma unroll
+      for (int r = 0; r < kPxPerFeThread; ++r) {
+        const unsigned m = __ballot_sync(0xffffffffu, ok[r]);
+        const int before = __popc(m & ((1u << lane) - 1u));
+        rank[r] = ok[r] ? before : (lane - before);  // rank among valid / among invalid of this (round, warp)
+        if (lane == 0) sm.cnt[r * kFeWarps + warp] = __popc(m);
+      }
+      // the M buffer we are about to overwrite must have been drained by the Gram warps
+      mbar_wait(&sm.m_empty[buf], ((i >> 1) & 1u) ^ 1u);
+      named_bar_sync(1, kFeThreads);
+      int nvalid = 0, base_valid[kPxPerFeThread], base_invalid[kPxPerFeThread];
+      {
+        int vb = 0, ib = 0;
+#pragma unroll
+        for (int r = 0; r < kPxPerFeThread; ++r)
+#pragma unroll
+          for (int w2 = 0; w2 < kFeWarps; ++w2) {
+            const int cvalid = sm.cnt[r * kFeWarps + w2];
+            if (w2 == warp) {
+              base_valid[r] = vb;
+              base_invalid[r] = ib;
+            }
+            vb += cvalid;
+            ib += 32 - cvalid;
+          }
+        nvalid = vb;
+      }
+      const int padded = (nvalid + 31) & ~31;
+      float* Mb = sm.M[buf];
+#pragma unroll
+      for (int r = 0; r < kPxPerFeThread; ++r) {
+        if (ok[r]) {
+          const int idx = base_valid[r] + rank[r];
+          const uint32_t s = r * kFeThreads + tid;
+          const float sc = feat[r][0];
+          if constexpr (C % 4 == 0 && C >= 4) {
+            constexpr int NV = C / 4;
+            const int rot = (NV >= 8) ? lane : (lane / (8 / (NV < 8 ? NV : 8)));
+            const float4* src = reinterpret_cast<const float4*>(&sm.jc[st][s * C]);
+#pragma unroll
+            for (int k4 = 0; k4 < NV; ++k4) {
+              const int kk4 = (k4 + rot) % NV;
+              const float4 v = src[kk4];
+              Mb[(kk4 * 4 + 0) * kTilePixels + idx] = sc * v.x;
+              Mb[(kk4 * 4 + 1) * kTilePixels + idx] = sc * v.y;
+              Mb[(kk4 * 4 + 2) * kTilePixels + idx] = sc * v.z;
+              Mb[(kk4 * 4 + 3) * kTilePixels + idx] = sc * v.w;
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < C; ++kk) Mb[kk * kTilePixels + idx] = sc * sm.jc[st][s * C + kk];
+          }
+#pragma unroll
+          for (int j = 0; j < 7; ++j) Mb[(C + j) * kTilePixels + idx] = feat[r][1 + j];
+#pragma unroll
+          for (int j = C + 7; j < NFP; ++j) Mb[j * kTilePixels + idx] = 0.0f;
+        } else {
+          const int idx = nvalid + base_invalid[r] + rank[r];
+          if (idx < padded) {
+#pragma unroll
+            for (int j = 0; j < NFP; ++j) Mb[j * kTilePixels + idx] = 0.0f;
+          }
+        }
+      }
+      if (tid == 0) {
+        sm.meta[buf].nvalid = nvalid;
+        sm.meta[buf].item_changed = changed ? 1 : 0;
+        sm.meta[buf].slot = (int)I.slot;
+      }
+      mbar_arrive(&sm.m_full[buf]);     // release: M tile + meta visible to the Gram warps
+      named_bar_sync(1, kFeThreads);    // all front-end threads are done with ring stage `st`
+      if (tid == 0) {
+        const int gn = g + kStages;
+        if (gn < g_hi) {
+          while ((uint32_t)gn >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
+          if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads<C>(sm, items, it_pf, gn, st);
+        }
+      }
+    }
+  } else if (warp < kFeWarps + NBLK) {
+    // ========================================================================= Gram warps
+    const int b = warp - kFeWarps;
+    // block index -> (bi, bj), bi <= bj, row-major over the upper triangle
+    int bi = 0, rem = b;
+    while (rem >= NB - bi) {
+      rem -= NB - bi;
+      ++bi;
+    }
+    const int bj = bi + rem;
+    float acc[64];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) acc[e] = 0.0f;
+    unsigned int inliers = 0;
+    int cur_slot = -1;
+
+    auto flush = [&](int slot) {
+      reduce_scatter64(acc, lane);
+      float* P = partials + (size_t)slot * Cfg::PARTIAL_FLOATS;
+      const int e0 = 2 * lane;  // entries e0, e0+1 of the 8x8 block: row e0/8, cols e0%8, e0%8+1
+      float2 v = make_float2(acc[0], acc[1]);
+      *reinterpret_cast<float2*>(&P[(8 * bi + (e0 >> 3)) * NFP + 8 * bj + (e0 & 7)]) = v;
+      if (b == 0 && lane == 0) reinterpret_cast<unsigned int*>(P)[NFP * NFP] = inliers;
+#pragma unroll
+      for (int e = 0; e < 64; ++e) acc[e] = 0.0f;
+      inliers = 0;
+    };
+
+    for (int g = g_lo, i = 0; g < g_hi; ++g, ++i) {
+      const int buf = i & 1;
+      mbar_wait(&sm.m_full[buf], (i >> 1) & 1u);
+      const TileMeta meta = sm.meta[buf];
+      if (meta.item_changed) {
+        if (cur_slot >= 0) flush(cur_slot);
+        cur_slot = meta.slot;
+      }
+      inliers += (unsigned)meta.nvalid;
+      const float* Mr = sm.M[buf] + (8 * bi) * kTilePixels + lane;
+      const float* Mc = sm.M[buf] + (8 * bj) * kTilePixels + lane;
+      const int steps = (meta.nvalid + 31) >> 5;
+      for (int s = 0; s < steps; ++s) {
+        float r[8], c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = Mr[j * kTilePixels + s * 32];
+        if (bi == bj) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) c[j] = r[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) c[j] = Mc[j * kTilePixels + s * 32];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[j * 8 + k] = fmaf(r[j], c[k], acc[j * 8 + k]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.m_empty[buf]);
+    }
+    if (cur_slot >= 0) flush(cur_slot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Finalize: fixed-order sum of the per-CTA partials + expansion to the (12+C) system.
+// grid = (num_items, C + 1): unit u < C is code row u (G[u][u..C-1], G[u][C..C+6]); unit C is the
+// 7x7 pose/residual block.  8 warps split the partial list; cross-warp sum in warp order.
+// Record layout: [JtJ packed upper (NP(NP+1)/2) | Jtr (NP) | residual | inliers (u32 bits)].
+// ------------------------------------------------------------------------------------------------
+constexpr int kFinWarps = 8;
+
+__device__ __forceinline__ int packed_index(int i, int j, int NP) { return i * NP - (i * (i - 1)) / 2 + (j - i); }
+
+template <int C>
+__global__ void __launch_bounds__(kFinWarps * 32)
+sfm_finalize_kernel(const SfmItemDev* __restrict__ items, const float* __restrict__ partials,
+                    float* __restrict__ records)
+{
+  using Cfg = SfmCfg<C>;
+  constexpr int NFP = Cfg::NFP;
+  constexpr int NP = 12 + C;
+  constexpr int NH = NP * (NP + 1) / 2;
+  constexpr int REC = NH + NP + 2;
+  constexpr int NE = (C + 7 > 49) ? (C + 7) : 49;  // entries per unit (code row: <= C+7, pose unit: 49)
+  constexpr int EPL = (NE + 31) / 32;              // entries per lane
+  __shared__ float red[kFinWarps][EPL * 32];
+  __shared__ unsigned int red_inl[kFinWarps];
+  __shared__ float sum[EPL * 32];
+
+  const SfmItemDev& I = items[blockIdx.x];
+  const int unit = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* P = partials + (size_t)I.partial_begin * Cfg::PARTIAL_FLOATS;
+  const int np = (int)I.num_ctas;
+
+  // entry e of the unit -> offset into the NFP x NFP partial matrix
+  int off[EPL];
+  bool act[EPL];
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) {
+    const int e = q * 32 + lane;
+    if (unit < C) {  // code row `unit`: columns unit .. C+6
+      act[q] = (unit + e) < (C + 7);
+      off[q] = unit * NFP + unit + e;
+    } else {  // pose block: rows/cols C..C+6 ; entry e -> (e / 7, e % 7), upper part only
+      const int r = e / 7, c = e - 7 * r;
+      act[q] = (e < 49) && (c >= r);
+      off[q] = (C + r) * NFP + C + c;
+    }
+  }
+  float part[EPL];
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) part[q] = 0.0f;
+  unsigned int inl = 0;
+  for (int k = warp; k < np; k += kFinWarps) {
+    const float* Pk = P + (size_t)k * Cfg::PARTIAL_FLOATS;
+#pragma unroll
+    for (int q = 0; q < EPL; ++q)
+      if (act[q]) part[q] += Pk[off[q]];
+    if (unit == C && lane == 0) inl += reinterpret_cast<const unsigned int*>(Pk)[NFP * NFP];
+  }
+#pragma unroll
+  for (int q = 0; q < EPL; ++q) red[warp][q * 32 + lane] = part[q];
+  if (lane == 0) red_inl[warp] = inl;
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < EPL; ++q) {
+      float s = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kFinWarps; ++w) s += red[w][q * 32 + lane];
+      sum[q * 32 + lane] = s;
+    }
+  }
+  __syncthreads();
+
+  float* rec = records + (size_t)blockIdx.x * REC;
+  float* JtJ = rec;
+  float* Jtr = rec + NH;
+  if (unit < C) {
+    const int c = unit;
+    // code-code: H[12+c][12+c'] = G[c][c'] , c' >= c
+    for (int e = threadIdx.x; e < C - c; e += blockDim.x) JtJ[packed_index(12 + c, 12 + c + e, NP)] = sum[e];
+    // pose-code: H[j][12+c] = sum_k P0[k][j] * G[a_k][c] ; H[6+j][12+c] with P1.  G[c][C+k] at entry (C - c) + k
+    if (threadIdx.x < 12) {
+      const int j = threadIdx.x % 6;
+      const float* Pm = threadIdx.x < 6 ? I.P0 : I.P1;
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s = fmaf(Pm[k * 6 + j], sum[(C - c) + k], s);
+      JtJ[packed_index(threadIdx.x, 12 + c, NP)] = s;
+    }
+    if (threadIdx.x == 12) Jtr[12 + c] = sum[(C - c) + 6];
+  } else {
+    // pose block: Gaa (6x6 symmetric, upper stored at sum[r*7+c]), Gar = sum[r*7+6], Grr = sum[48]
+    __shared__ float Gaa[6][6];
+    __shared__ float T0[6][6];  // Gaa * P0
+    __shared__ float T1[6][6];  // Gaa * P1
+    if (threadIdx.x < 36) {
+      const int r = threadIdx.x / 6, c = threadIdx.x % 6;
+      Gaa[r][c] = (c >= r) ? sum[r * 7 + c] : sum[c * 7 + r];
+    }
+    __syncthreads();
+    if (threadIdx.x < 72) {
+      const int m = threadIdx.x / 36, r = (threadIdx.x % 36) / 6, c = threadIdx.x % 6;
+      const float* Pm = m ? I.P1 : I.P0;
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s = fmaf(Gaa[r][k], Pm[k * 6 + c], s);
+      (m ? T1 : T0)[r][c] = s;
+    }
+    __syncthreads();
+    // H[i][j] for the 12x12 pose part, i <= j:  Pa^T * Gaa * Pb
+    for (int e = threadIdx.x; e < 144; e += blockDim.x) {
+      const int i = e / 12, j = e % 12;
+      if (j < i) continue;
+      const float* Pa = (i < 6) ? I.P0 : I.P1;
+      const float(*Tb)[6] = (j < 6) ? T0 : T1;
+      const int ii = i % 6, jj = j % 6;
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s = fmaf(Pa[k * 6 + ii], Tb[k][jj], s);
+      JtJ[packed_index(i, j, NP)] = s;
+    }
+    if (threadIdx.x >= 160 && threadIdx.x < 172) {
+      const int i = threadIdx.x - 160;
+      const float* Pa = (i < 6) ? I.P0 : I.P1;
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s = fmaf(Pa[k * 6 + (i % 6)], sum[k * 7 + 6], s);
+      Jtr[i] = s;
+    }
+    if (threadIdx.x == 192) {
+      unsigned int tot = 0;
+      for (int w = 0; w < kFinWarps; ++w) tot += red_inl[w];
+      rec[NH + NP] = sum[48];
+      reinterpret_cast<unsigned int*>(rec)[NH + NP + 1] = tot;
+    }
+  }
+}
+
+template <int C>
+cudaError_t launch_impl(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, float* partials_dev,
+                        float* records_dev, cudaStream_t stream)
+{
+  using Cfg = SfmCfg<C>;
+  const size_t smem = sizeof(Smem<C>);
+  cudaError_t err = cudaFuncSetAttribute(sfm_step_fp32_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+  if (err != cudaSuccess) return err;
+  const int threads = (kFeWarps + Cfg::NBLK) * 32;
+  sfm_step_fp32_kernel<C><<<plan.num_ctas, threads, smem, stream>>>(items_dev, plan.num_items, plan.num_tiles,
+                                                                    partials_dev);
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  dim3 grid(plan.num_items, C + 1);
+  sfm_finalize_kernel<C><<<grid, kFinWarps * 32, 0, stream>>>(items_dev, partials_dev, records_dev);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool sfm_fp32_supported(int code_size) { return code_size == 8 || code_size == 16 || code_size == 32; }
+
+size_t sfm_partial_floats(int code_size)
+{
+  switch (code_size) {
+    case 8: return SfmCfg<8>::PARTIAL_FLOATS;
+    case 16: return SfmCfg<16>::PARTIAL_FLOATS;
+    case 32: return SfmCfg<32>::PARTIAL_FLOATS;
+    default: return 0;
+  }
+}
+
+int sfm_max_ctas()
+{
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 1;
+}
+
+cudaError_t launch_sfm_fp32(int code_size, const SfmItemDev* items_dev, const SfmLaunchPlan& plan,
+                            float* partials_dev, float* records_dev, cudaStream_t stream)
+{
+  switch (code_size) {
+    case 8: return launch_impl<8>(items_dev, plan, partials_dev, records_dev, stream);
+    case 16: return launch_impl<16>(items_dev, plan, partials_dev, records_dev, stream);
+    case 32: return launch_impl<32>(items_dev, plan, partials_dev, records_dev, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace dfk

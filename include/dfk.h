@@ -1,0 +1,199 @@
+/*
+ * dfk.h -- C ABI of libdfk.so: B200-native (sm_100a) replacement for the dense
+ * alignment hot path of DeepFactors' libdf_cuda.so (sources/cuda).
+ *
+ * The reference exports C++ class templates over Sophus/Eigen/VisionCore types
+ * (not a C ABI); this header is the plain-pointer core a maintainer binds from
+ * thin wrappers (see INTEGRATION.md and the headers under include/df/ for the C++ facade that
+ * reproduces df::SfmAligner / df::SE3Aligner on top of it).  Every entry point
+ * cites the reference interface it replaces; citations are file:line into
+ * jczarnowski/DeepFactors @ bffc78a.
+ *
+ * Conventions
+ *   pose      float[7] in Sophus::SE3f::data() order: unit quaternion (x,y,z,w),
+ *             translation (x,y,z).
+ *   DfkImage  pitched 2-D device view, the stand-in for vc::Image2DView /
+ *             vc::Buffer2DView: element (x,y) at (char*)ptr + y*pitch_bytes +
+ *             x*elem_size.  `width` counts PIXELS for every kind of image:
+ *               scalar images (img, dpt, std, valid, prx_orig): 1 float / pixel
+ *               grad1: 2 floats / pixel (gx,gy), Eigen::Matrix<float,1,2>
+ *               prx_jac: code_size contiguous floats / pixel
+ *                        (sources/core/mapping/keyframe.h:52, dense_sfm.h:150;
+ *                        the reference views it as a (W*CS) x H float image)
+ *   results   JtJ is the packed upper triangle, row major: (i,j), i<=j, at
+ *             i*NP - i*(i-1)/2 + (j-i); column order [pose0 t(3) w(3) | pose1
+ *             t(3) w(3) | code(C)] (dense_sfm.h:163-177).  Jtr is NOT negated,
+ *             residual is the raw sum of squared weighted residuals
+ *             (photometric_factor.cpp:105-106,275-282 do the sign flip/rescale).
+ *   errors    every call returns a DfkStatus; dfk_last_error(handle) returns the
+ *             message the reference would have thrown (launch_utils.h:26-32
+ *             vc::CUDAException, cu_sfmaligner.cpp:171-173 std::runtime_error).
+ *   threads   a handle is not re-entrant; different handles are independent
+ *             (parameters are kernel arguments, not a process-global __constant__
+ *             as in cu_sfmaligner.cpp:34,111).
+ */
+#ifndef DFK_H_
+#define DFK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFK_VERSION 100
+
+typedef enum {
+  DFK_OK = 0,
+  DFK_ERR_INVALID_ARG = 1, /* glog CHECK failures of the reference (cu_sfmaligner.cpp:190-191) */
+  DFK_ERR_CUDA = 2,        /* vc::CUDAException (launch_utils.h:26-32) */
+  DFK_ERR_UNSUPPORTED = 3, /* code size / layout this build has no kernel for */
+  DFK_ERR_NOMEM = 4
+} DfkStatus;
+
+typedef struct DfkContext* DfkHandle;
+
+/* vc::Image2DView<T, TargetDeviceCUDA> stand-in (VisionCore, not in tree; call sites dense_sfm.h:141-147) */
+typedef struct {
+  void* ptr;
+  size_t pitch_bytes;
+  uint32_t width;  /* pixels */
+  uint32_t height; /* rows   */
+} DfkImage;
+
+/* df::PinholeCamera<float> (sources/common/algorithm/pinhole_camera.h:43, _impl.h:30-31) */
+typedef struct {
+  float fx, fy, u0, v0;
+  float width, height;
+} DfkCamera;
+
+/* df::DenseSfmParams (sources/common/algorithm/dense_sfm.h:36-43), same defaults */
+typedef struct {
+  float huber_delta; /* 0.1  */
+  float ocl_th;      /* 1000, unused by the reference */
+  float avg_dpt;     /* 2.0  */
+  float min_dpt;     /* 0.0  */
+  int32_t valid_border; /* 2 */
+} DfkDenseSfmParams;
+
+/* df::SfmAlignerParams (sources/cuda/cu_sfmaligner.h:41-48).  The launch-shape members are
+ * accepted for source compatibility and validated like the reference (threads % 32 == 0,
+ * blocks <= 1024; cu_sfmaligner.cpp:187-203) but the kernels size their own grids. */
+typedef struct {
+  DfkDenseSfmParams sfmparams;
+  int32_t step_threads; /* 32  */
+  int32_t step_blocks;  /* 11  */
+  int32_t eval_threads; /* 224 */
+  int32_t eval_blocks;  /* 66  */
+} DfkSfmAlignerParams;
+
+/* How the (6+C)x(6+C) Gauss-Newton Gram is accumulated.
+ *   DFK_GRAM_FP32     CUDA-core FFMA, fp32 products and sums (any supported code size)
+ *   DFK_GRAM_TF32X3   tcgen05 tensor cores, split-precision tf32 (hi*hi + lo*hi + hi*lo),
+ *                     fp32 accumulate in TMEM; code size >= 32 only
+ *   DFK_GRAM_AUTO     tensor cores where available for the code size, else FP32 */
+typedef enum { DFK_GRAM_AUTO = 0, DFK_GRAM_FP32 = 1, DFK_GRAM_TF32X3 = 2 } DfkGramMode;
+
+/* ------------------------------------------------------------------ lifetime / config */
+
+/* Replaces SfmAligner::SfmAligner / SE3Aligner::SE3Aligner (cu_sfmaligner.cpp:102-114,
+ * cu_se3aligner.cpp:119-120): owns the reduction scratch (bscratch_) and a stream.
+ * device < 0 => current device. */
+DfkStatus dfk_create(int device, DfkHandle* out);
+DfkStatus dfk_destroy(DfkHandle h);
+/* cudaStream_t to launch on (NULL = the handle's own stream).  The reference uses the
+ * default stream + cudaDeviceSynchronize (launch_utils.h:28). */
+DfkStatus dfk_set_stream(DfkHandle h, void* cuda_stream);
+void* dfk_get_stream(DfkHandle h);
+DfkStatus dfk_synchronize(DfkHandle h);
+const char* dfk_last_error(DfkHandle h);
+const char* dfk_status_string(DfkStatus s);
+int dfk_version(void);
+/* 1 if this build has a RunStep kernel for the code size (reference: only 32, cu_sfmaligner.cpp:209) */
+int dfk_sfm_supports_code_size(int code_size);
+
+/* SfmAligner ctor params + SetEvalThreadsBlocks/SetStepThreadsBlocks (cu_sfmaligner.cpp:187-203) */
+DfkStatus dfk_sfm_set_params(DfkHandle h, const DfkSfmAlignerParams* p);
+DfkStatus dfk_sfm_get_params(DfkHandle h, DfkSfmAlignerParams* p);
+DfkStatus dfk_sfm_set_gram_mode(DfkHandle h, DfkGramMode m);
+/* SE3Aligner::SetHuberDelta (cu_se3aligner.h:72), default 0.1 (:85) */
+DfkStatus dfk_se3_set_huber_delta(DfkHandle h, float v);
+
+/* ------------------------------------------------------------------ SfmAligner */
+
+/* SfmAligner<float,CS>::RunStep (cu_sfmaligner.h:76-86, cu_sfmaligner.cpp:149-185).
+ * code0/std0 are accepted and ignored exactly as the reference kernel ignores them
+ * (dense_sfm.h:56-67,133-201); both may be NULL.  valid0 is in/out: set to 1 where a
+ * correspondence is valid, never cleared (dense_sfm.h:161).  Synchronous; results land in
+ * host memory: JtJ[NP(NP+1)/2], Jtr[NP], NP = 12 + code_size. */
+DfkStatus dfk_sfm_run_step(DfkHandle h, const float pose0[7], const float pose1[7],
+                           const float* code0, int code_size, const DfkCamera* cam,
+                           const DfkImage* img0, const DfkImage* img1, const DfkImage* dpt0,
+                           const DfkImage* std0, const DfkImage* valid0, const DfkImage* prx0_jac,
+                           const DfkImage* grad1,
+                           float* JtJ, float* Jtr, float* residual, uint64_t* inliers);
+
+/* SfmAligner<float,CS>::EvaluateError (cu_sfmaligner.h:67-74, cu_sfmaligner.cpp:120-147):
+ * border 1 / min_dpt 0 (dense_sfm.h:91), Huber-weighted squared error + inlier count.
+ * std0/grad1 feed only the dead uncertainty weight (dense_sfm.h:100-107); may be NULL. */
+DfkStatus dfk_sfm_evaluate_error(DfkHandle h, const float pose0[7], const float pose1[7],
+                                 const DfkCamera* cam, const DfkImage* img0, const DfkImage* img1,
+                                 const DfkImage* dpt0, const DfkImage* std0, const DfkImage* grad1,
+                                 float* residual, uint64_t* inliers);
+
+/* One (keyframe, frame, pyramid level) evaluation of a batch: the unit PhotometricFactor
+ * creates per pair and level (sources/core/mapping/df_work.cpp:211-225). */
+typedef struct {
+  float pose0[7];
+  float pose1[7];
+  DfkCamera cam;
+  DfkImage img0, img1, dpt0, valid0, prx0_jac, grad1;
+} DfkSfmWorkItem;
+
+/* floats per device result record for code size C: [JtJ packed | Jtr | residual | inliers(u32 bits)] */
+#define DFK_SFM_NP(C) (12 + (C))
+#define DFK_SFM_RECORD_FLOATS(C) (DFK_SFM_NP(C) * (DFK_SFM_NP(C) + 1) / 2 + DFK_SFM_NP(C) + 2)
+
+/* Batched RunStep: n work items in one persistent launch (the reference evaluates them one
+ * call at a time from ISAM2, mapper.cpp:518-519).  `items` is a HOST array; `records_dev`
+ * is DEVICE memory, n * DFK_SFM_RECORD_FLOATS(code_size) floats.  Asynchronous on the
+ * handle's stream (no host sync, no D2H). */
+DfkStatus dfk_sfm_run_step_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size,
+                                 float* records_dev);
+/* Same, then copies the records to host memory and synchronizes. */
+DfkStatus dfk_sfm_run_step_batch_host(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size,
+                                      float* records_host);
+
+/* ------------------------------------------------------------------ SE3Aligner */
+
+/* SE3Aligner<float>::RunStep (cu_se3aligner.h:65-70, cu_se3aligner.cpp:153-176):
+ * JtJ[21] packed upper 6x6, Jtr[6]. */
+DfkStatus dfk_se3_run_step(DfkHandle h, const float se3[7], const DfkCamera* cam,
+                           const DfkImage* img0, const DfkImage* img1, const DfkImage* dpt0,
+                           const DfkImage* grad1,
+                           float* JtJ, float* Jtr, float* residual, uint64_t* inliers);
+
+/* SE3Aligner<float>::Warp (cu_se3aligner.h:58-63, cu_se3aligner.cpp:125-151): renders img1
+ * into frame 0 (img2, 0 where invalid); residual = SIGNED sum(img0 - sampled) (:106). */
+DfkStatus dfk_se3_warp(DfkHandle h, const float se3[7], const DfkCamera* cam,
+                       const DfkImage* img0, const DfkImage* img1, const DfkImage* dpt0,
+                       const DfkImage* img2, float* residual, uint64_t* inliers);
+
+/* ------------------------------------------------------------------ cu_image_proc free functions */
+
+/* df::UpdateDepth (cu_image_proc.h:41-44, cu_image_proc.cpp:248-277):
+ * dpt = avg/(prx_orig + prx_jac . code) - avg.  code is HOST memory. Asynchronous. */
+DfkStatus dfk_update_depth(DfkHandle h, const float* code, int code_size, const DfkImage* prx_orig,
+                           const DfkImage* prx_jac, float avg_dpt, const DfkImage* dpt_out);
+/* df::SobelGradients (cu_image_proc.h:27-29, cu_image_proc.cpp:57-113). Asynchronous. */
+DfkStatus dfk_sobel_gradients(DfkHandle h, const DfkImage* img, const DfkImage* grad);
+/* df::GaussianBlurDown (cu_image_proc.h:31-33, cu_image_proc.cpp:134-184). Asynchronous. */
+DfkStatus dfk_gaussian_blur_down(DfkHandle h, const DfkImage* in, const DfkImage* out);
+/* df::SquaredError (cu_image_proc.h:35-39, cu_image_proc.cpp:190-242). Synchronous. */
+DfkStatus dfk_squared_error(DfkHandle h, const DfkImage* a, const DfkImage* b, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFK_H_ */

@@ -1,0 +1,280 @@
+"""ctypes front-end of the CPU oracle (oracle/libdfk_oracle.so).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/dfk_oracle.h.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / `--impl reference` legs may import this module.  PARITY
+UNPINNED: the reference cannot be built here (Eigen/Sophus/VisionCore absent) and ships no
+golden vectors; see the header of dfk_oracle.h.
+
+All arrays are numpy float32, C-contiguous rows; `pitch` is derived from strides and counted in
+floats.  Images are [H, W]; grad1 is [H, W, 2]; prx_jac is [H, W, C].
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdfk_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc, -O2 -ffp-contract=off)."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in ("dfk_oracle.c", "dfk_oracle_impl.inc", "dfk_oracle.h", "Makefile")
+    ):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return _LIB_PATH
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("u0", C.c_float), ("v0", C.c_float),
+                ("width", C.c_float), ("height", C.c_float)]
+
+
+class SfmParams(C.Structure):
+    _fields_ = [("huber_delta", C.c_float), ("ocl_th", C.c_float), ("avg_dpt", C.c_float),
+                ("min_dpt", C.c_float), ("valid_border", C.c_int)]
+
+
+def default_params(**kw) -> SfmParams:
+    p = SfmParams(0.1, 1000.0, 2.0, 0.0, 2)  # dense_sfm.h:36-43
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.dfko_omp_max_threads.restype = C.c_int
+        _lib.dfko_squared_error_f.restype = C.c_float
+        _lib.dfko_squared_error_d.restype = C.c_double
+    return _lib
+
+
+def _f32(a):
+    a = np.asarray(a)
+    assert a.dtype == np.float32, a.dtype
+    return a
+
+
+def _ptr(a, ctype=C.c_float):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _pitch(a):
+    """row pitch in floats of an [H, W(, K)] array whose rows are contiguous"""
+    assert a.strides[-1] == a.itemsize
+    if a.ndim == 3:
+        assert a.strides[1] == a.itemsize * a.shape[2]
+    assert a.strides[0] % a.itemsize == 0
+    return C.c_size_t(a.strides[0] // a.itemsize)
+
+
+def _cam(cam) -> Camera:
+    if isinstance(cam, Camera):
+        return cam
+    return Camera(cam.fx, cam.fy, cam.u0, cam.v0, cam.width, cam.height)
+
+
+@dataclass
+class StepResult:
+    JtJ: np.ndarray  # packed upper, NP(NP+1)/2
+    Jtr: np.ndarray
+    residual: float
+    inliers: int
+
+    @property
+    def NP(self):
+        return self.Jtr.shape[0]
+
+    def dense(self) -> np.ndarray:
+        n = self.NP
+        H = np.zeros((n, n), dtype=self.JtJ.dtype)
+        H[np.triu_indices(n)] = self.JtJ
+        return H + np.triu(H, 1).T
+
+
+def so3_exp(omega, dtype=np.float64):
+    omega = np.ascontiguousarray(omega, dtype=dtype)
+    q = np.zeros(4, dtype=dtype)
+    fn = lib().dfko_so3_exp_d if dtype == np.float64 else lib().dfko_so3_exp_f
+    ct = C.c_double if dtype == np.float64 else C.c_float
+    fn(_ptr(omega, ct), _ptr(q, ct))
+    return q
+
+
+def pose_perturb(pose, idx, eps, dtype=np.float64):
+    pose = np.ascontiguousarray(pose, dtype=dtype)
+    out = np.zeros(7, dtype=dtype)
+    if dtype == np.float64:
+        lib().dfko_pose_perturb_d(_ptr(pose, C.c_double), C.c_int(idx), C.c_double(eps), _ptr(out, C.c_double))
+    else:
+        lib().dfko_pose_perturb_f(_ptr(pose, C.c_float), C.c_int(idx), C.c_float(eps), _ptr(out, C.c_float))
+    return out
+
+
+def relative_pose(a, b, dtype=np.float64, jacobians=True):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    b = np.ascontiguousarray(b, dtype=dtype)
+    ab = np.zeros(7, dtype=dtype)
+    ja = np.zeros(36, dtype=dtype)
+    jb = np.zeros(36, dtype=dtype)
+    ct = C.c_double if dtype == np.float64 else C.c_float
+    fn = lib().dfko_relative_pose_d if dtype == np.float64 else lib().dfko_relative_pose_f
+    fn(_ptr(a, ct), _ptr(b, ct), _ptr(ab, ct), _ptr(ja, ct) if jacobians else None, _ptr(jb, ct) if jacobians else None)
+    return ab, ja.reshape(6, 6), jb.reshape(6, 6)
+
+
+def probe_pixel(x, y, dpt, cam, pose, border=1, min_dpt=0.0, avg_dpt=2.0):
+    pose = np.ascontiguousarray(pose, dtype=np.float64)
+    out = np.zeros(17, dtype=np.float64)
+    c = _cam(cam)
+    lib().dfko_probe_pixel_d(C.c_double(x), C.c_double(y), C.c_double(dpt), C.byref(c), _ptr(pose, C.c_double),
+                             C.c_int(border), C.c_double(min_dpt), C.c_double(avg_dpt), _ptr(out, C.c_double))
+    return dict(valid=bool(out[0]), pix1=out[1:3].copy(), J_pose=out[3:15].reshape(2, 6).copy(),
+                J_prx=out[15:17].copy())
+
+
+def sfm_run_step(pose0, pose1, cam, img0, img1, dpt0, valid0, prx0_jac, grad1, params=None, *,
+                 precision="f32", loop_order=0, omp_threads=None) -> StepResult:
+    """SfmAligner::RunStep on the CPU.  precision: "f32" (reference-like) or "f64" (truth).
+    omp_threads: if not None, use the OpenMP row-major float variant (CPU baseline)."""
+    params = params or default_params()
+    img0, img1, dpt0, prx0_jac, grad1 = map(_f32, (img0, img1, dpt0, prx0_jac, grad1))
+    H, W = img0.shape
+    Cs = prx0_jac.shape[2]
+    assert prx0_jac.shape[:2] == (H, W) and grad1.shape == (H, W, 2)
+    NP = 12 + Cs
+    pose0 = np.ascontiguousarray(pose0, dtype=np.float32)
+    pose1 = np.ascontiguousarray(pose1, dtype=np.float32)
+    c = _cam(cam)
+    inl = C.c_uint64(0)
+    vptr, vpitch = (None, C.c_size_t(0)) if valid0 is None else (_ptr(_f32(valid0)), _pitch(valid0))
+    common = (_ptr(pose0), _ptr(pose1), C.c_int(Cs), C.byref(c), C.c_int(W), C.c_int(H),
+              _ptr(img0), _pitch(img0), _ptr(img1), _pitch(img1), _ptr(dpt0), _pitch(dpt0), vptr, vpitch,
+              _ptr(prx0_jac), _pitch(prx0_jac), _ptr(grad1), _pitch(grad1), C.byref(params))
+    if precision == "f64":
+        JtJ = np.zeros(NP * (NP + 1) // 2, dtype=np.float64)
+        Jtr = np.zeros(NP, dtype=np.float64)
+        res = C.c_double(0)
+        lib().dfko_sfm_run_step_d(*common, C.c_int(loop_order), _ptr(JtJ, C.c_double), _ptr(Jtr, C.c_double),
+                                  C.byref(res), C.byref(inl))
+    else:
+        JtJ = np.zeros(NP * (NP + 1) // 2, dtype=np.float32)
+        Jtr = np.zeros(NP, dtype=np.float32)
+        res = C.c_float(0)
+        if omp_threads is not None:
+            lib().dfko_sfm_run_step_f_omp(*common, C.c_int(omp_threads), _ptr(JtJ), _ptr(Jtr), C.byref(res),
+                                          C.byref(inl))
+        else:
+            lib().dfko_sfm_run_step_f(*common, C.c_int(loop_order), _ptr(JtJ), _ptr(Jtr), C.byref(res), C.byref(inl))
+    return StepResult(JtJ, Jtr, float(res.value), int(inl.value))
+
+
+def sfm_evaluate_error(pose0, pose1, cam, img0, img1, dpt0, params=None, *, precision="f32"):
+    params = params or default_params()
+    img0, img1, dpt0 = map(_f32, (img0, img1, dpt0))
+    H, W = img0.shape
+    pose0 = np.ascontiguousarray(pose0, dtype=np.float32)
+    pose1 = np.ascontiguousarray(pose1, dtype=np.float32)
+    c = _cam(cam)
+    inl = C.c_uint64(0)
+    args = (_ptr(pose0), _ptr(pose1), C.byref(c), C.c_int(W), C.c_int(H), _ptr(img0), _pitch(img0), _ptr(img1),
+            _pitch(img1), _ptr(dpt0), _pitch(dpt0), C.byref(params))
+    if precision == "f64":
+        res = C.c_double(0)
+        lib().dfko_sfm_evaluate_error_d(*args, C.byref(res), C.byref(inl))
+    else:
+        res = C.c_float(0)
+        lib().dfko_sfm_evaluate_error_f(*args, C.byref(res), C.byref(inl))
+    return float(res.value), int(inl.value)
+
+
+def se3_run_step(se3, cam, img0, img1, dpt0, grad1, huber_delta=0.1, *, precision="f32") -> StepResult:
+    img0, img1, dpt0, grad1 = map(_f32, (img0, img1, dpt0, grad1))
+    H, W = img0.shape
+    se3 = np.ascontiguousarray(se3, dtype=np.float32)
+    c = _cam(cam)
+    inl = C.c_uint64(0)
+    args = (_ptr(se3), C.byref(c), C.c_int(W), C.c_int(H), _ptr(img0), _pitch(img0), _ptr(img1), _pitch(img1),
+            _ptr(dpt0), _pitch(dpt0), _ptr(grad1), _pitch(grad1), C.c_float(huber_delta))
+    if precision == "f64":
+        JtJ = np.zeros(21, dtype=np.float64)
+        Jtr = np.zeros(6, dtype=np.float64)
+        res = C.c_double(0)
+        lib().dfko_se3_run_step_d(*args, _ptr(JtJ, C.c_double), _ptr(Jtr, C.c_double), C.byref(res), C.byref(inl))
+    else:
+        JtJ = np.zeros(21, dtype=np.float32)
+        Jtr = np.zeros(6, dtype=np.float32)
+        res = C.c_float(0)
+        lib().dfko_se3_run_step_f(*args, _ptr(JtJ), _ptr(Jtr), C.byref(res), C.byref(inl))
+    return StepResult(JtJ, Jtr, float(res.value), int(inl.value))
+
+
+def se3_warp(se3, cam, img0, img1, dpt0, *, precision="f32"):
+    img0, img1, dpt0 = map(_f32, (img0, img1, dpt0))
+    H, W = img0.shape
+    se3 = np.ascontiguousarray(se3, dtype=np.float32)
+    img2 = np.zeros((H, W), dtype=np.float32)
+    c = _cam(cam)
+    inl = C.c_uint64(0)
+    args = (_ptr(se3), C.byref(c), C.c_int(W), C.c_int(H), _ptr(img0), _pitch(img0), _ptr(img1), _pitch(img1),
+            _ptr(dpt0), _pitch(dpt0), _ptr(img2), _pitch(img2))
+    if precision == "f64":
+        res = C.c_double(0)
+        lib().dfko_se3_warp_d(*args, C.byref(res), C.byref(inl))
+    else:
+        res = C.c_float(0)
+        lib().dfko_se3_warp_f(*args, C.byref(res), C.byref(inl))
+    return img2, float(res.value), int(inl.value)
+
+
+def update_depth(code, prx_orig, prx_jac, avg_dpt=2.0):
+    code = np.ascontiguousarray(code, dtype=np.float32)
+    prx_orig, prx_jac = _f32(prx_orig), _f32(prx_jac)
+    H, W = prx_orig.shape
+    out = np.zeros((H, W), dtype=np.float32)
+    lib().dfko_update_depth_f(_ptr(code), C.c_int(code.shape[0]), C.c_int(W), C.c_int(H), _ptr(prx_orig),
+                              _pitch(prx_orig), _ptr(prx_jac), _pitch(prx_jac), C.c_float(avg_dpt), _ptr(out),
+                              _pitch(out))
+    return out
+
+
+def sobel_gradients(img):
+    img = _f32(img)
+    H, W = img.shape
+    grad = np.zeros((H, W, 2), dtype=np.float32)
+    lib().dfko_sobel_gradients_f(C.c_int(W), C.c_int(H), _ptr(img), _pitch(img), _ptr(grad), _pitch(grad))
+    return grad
+
+
+def gaussian_blur_down(img):
+    img = _f32(img)
+    H, W = img.shape
+    out = np.zeros((H // 2, W // 2), dtype=np.float32)  # camera_pyramid.h:43-44 integer halving
+    lib().dfko_gaussian_blur_down_f(C.c_int(W), C.c_int(H), _ptr(img), _pitch(img), C.c_int(W // 2), C.c_int(H // 2),
+                                    _ptr(out), _pitch(out))
+    return out
+
+
+def squared_error(a, b, precision="f32"):
+    a, b = _f32(a), _f32(b)
+    H, W = a.shape
+    fn = lib().dfko_squared_error_d if precision == "f64" else lib().dfko_squared_error_f
+    return float(fn(C.c_int(W), C.c_int(H), _ptr(a), _pitch(a), _ptr(b), _pitch(b)))
+
+
+def omp_max_threads() -> int:
+    return int(lib().dfko_omp_max_threads())

@@ -63,12 +63,15 @@ SYMBOLS = {
     "dfk_create": (C.c_int, [C.c_int, C.POINTER(_H)]),
     "dfk_destroy": (C.c_int, [_H]),
     "dfk_set_stream": (C.c_int, [_H, C.c_void_p]),
+    "dfk_use_own_stream": (C.c_int, [_H]),
     "dfk_get_stream": (C.c_void_p, [_H]),
     "dfk_synchronize": (C.c_int, [_H]),
     "dfk_last_error": (C.c_char_p, [_H]),
     "dfk_status_string": (C.c_char_p, [C.c_int]),
     "dfk_version": (C.c_int, []),
     "dfk_sfm_supports_code_size": (C.c_int, [C.c_int]),
+    "dfk_set_profiling": (C.c_int, [_H, C.c_int]),
+    "dfk_get_profile": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "dfk_sfm_set_params": (C.c_int, [_H, C.POINTER(DfkSfmAlignerParams)]),
     "dfk_sfm_get_params": (C.c_int, [_H, C.POINTER(DfkSfmAlignerParams)]),
     "dfk_sfm_set_gram_mode": (C.c_int, [_H, C.c_int]),

@@ -42,6 +42,14 @@ struct DfkContext {
   float* records_host = nullptr;  // pinned
   size_t records_host_cap = 0;
   std::vector<SfmItemDev> items_host;
+
+  // measurement hooks (dfk_set_profiling / dfk_get_profile)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;  // pairs: [2k] start, [2k+1] stop
+  size_t ev_used = 0;                // number of pairs recorded since the last read
+  double ev_ms_accum = 0.0;          // time of pairs already drained
+  uint64_t ev_count_accum = 0;
+  uint64_t launches = 0;
 };
 
 namespace {
@@ -279,6 +287,40 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
   return DFK_OK;
 }
 
+constexpr size_t kMaxEventPairs = 8192;
+
+// drains recorded event pairs into the accumulators (synchronizes the stream)
+DfkStatus drain_events(DfkHandle h)
+{
+  if (h->ev_used == 0) return DFK_OK;
+  DFK_CUDA(h, cudaStreamSynchronize(h->stream), "profiling: stream synchronize failed");
+  for (size_t k = 0; k < h->ev_used; ++k) {
+    float ms = 0.f;
+    DFK_CUDA(h, cudaEventElapsedTime(&ms, h->ev_pool[2 * k], h->ev_pool[2 * k + 1]), "profiling: event read failed");
+    h->ev_ms_accum += ms;
+  }
+  h->ev_count_accum += h->ev_used;
+  h->ev_used = 0;
+  return DFK_OK;
+}
+
+DfkStatus profile_events(DfkHandle h, cudaEvent_t* e0, cudaEvent_t* e1)
+{
+  if (h->ev_used == kMaxEventPairs) {
+    DfkStatus st = drain_events(h);
+    if (st != DFK_OK) return st;
+  }
+  while (h->ev_pool.size() < 2 * (h->ev_used + 1)) {
+    cudaEvent_t e;
+    DFK_CUDA(h, cudaEventCreate(&e), "profiling: event creation failed");
+    h->ev_pool.push_back(e);
+  }
+  *e0 = h->ev_pool[2 * h->ev_used];
+  *e1 = h->ev_pool[2 * h->ev_used + 1];
+  h->ev_used += 1;
+  return DFK_OK;
+}
+
 DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, float* records_dev)
 {
   if (!h) return DFK_ERR_INVALID_ARG;
@@ -298,8 +340,14 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
   DFK_CUDA(h, cudaMemcpyAsync(h->items_dev, h->items_host.data(), sizeof(SfmItemDev) * n, cudaMemcpyHostToDevice,
                               h->stream),
            "[SfmAligner::RunStep] work list upload failed");
-  DFK_CUDA(h, launch_sfm_fp32(code_size, h->items_dev, plan, h->partials_dev, records_dev, h->stream),
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (h->profiling) {
+    DfkStatus ps = profile_events(h, &ev0, &ev1);
+    if (ps != DFK_OK) return ps;
+  }
+  DFK_CUDA(h, launch_sfm_fp32(code_size, h->items_dev, plan, h->partials_dev, records_dev, h->stream, ev0, ev1),
            "[SfmAligner::RunStep] kernel launch failed");
+  h->launches += 2;  // step kernel + finalize kernel
   return DFK_OK;
 }
 
@@ -368,6 +416,7 @@ DfkStatus dfk_destroy(DfkHandle h)
   cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev);
   if (h->out_host) cudaFreeHost(h->out_host);
   if (h->records_host) cudaFreeHost(h->records_host);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return DFK_OK;
@@ -376,7 +425,14 @@ DfkStatus dfk_destroy(DfkHandle h)
 DfkStatus dfk_set_stream(DfkHandle h, void* cuda_stream)
 {
   if (!h) return DFK_ERR_INVALID_ARG;
-  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  return DFK_OK;
+}
+
+DfkStatus dfk_use_own_stream(DfkHandle h)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  h->stream = h->own_stream;
   return DFK_OK;
 }
 
@@ -391,6 +447,29 @@ DfkStatus dfk_synchronize(DfkHandle h)
 }
 
 const char* dfk_last_error(DfkHandle h) { return h ? h->err.c_str() : "null handle"; }
+
+DfkStatus dfk_set_profiling(DfkHandle h, int enabled)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  h->profiling = enabled != 0;
+  return DFK_OK;
+}
+
+DfkStatus dfk_get_profile(DfkHandle h, double* main_kernel_ms, uint64_t* main_kernel_launches,
+                          uint64_t* total_kernel_launches)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  DeviceGuard guard(h->device);
+  DfkStatus st = drain_events(h);
+  if (st != DFK_OK) return st;
+  if (main_kernel_ms) *main_kernel_ms = h->ev_ms_accum;
+  if (main_kernel_launches) *main_kernel_launches = h->ev_count_accum;
+  if (total_kernel_launches) *total_kernel_launches = h->launches;
+  h->ev_ms_accum = 0.0;
+  h->ev_count_accum = 0;
+  h->launches = 0;
+  return DFK_OK;
+}
 
 DfkStatus dfk_sfm_set_params(DfkHandle h, const DfkSfmAlignerParams* p)
 {
@@ -490,6 +569,7 @@ DfkStatus dfk_sfm_run_step(DfkHandle h, const float pose0[7], const float pose1[
 
 static DfkStatus fetch_out(DfkHandle h, int nfloats, const char* what)
 {
+  h->launches += 1;
   DFK_CUDA(h, cudaMemcpyAsync(h->out_host, h->out_dev, sizeof(float) * nfloats, cudaMemcpyDeviceToHost, h->stream),
            what);
   DFK_CUDA(h, cudaStreamSynchronize(h->stream), what);
@@ -594,6 +674,7 @@ DfkStatus dfk_update_depth(DfkHandle h, const float* code, int code_size, const 
   DFK_CUDA(h, launch_update_depth(h->code_dev, code_size, (int)W, (int)H, view_of(prx_orig), view_of(prx_jac),
                                   avg_dpt, (float*)dpt_out->ptr, (uint32_t)(dpt_out->pitch_bytes / 4), h->stream),
            "[UpdateDepth] kernel launch failed");
+  h->launches += 1;
   return DFK_OK;
 }
 
@@ -608,6 +689,7 @@ DfkStatus dfk_sobel_gradients(DfkHandle h, const DfkImage* img, const DfkImage* 
   DFK_CUDA(h, launch_sobel((int)W, (int)H, view_of(img), (float*)grad->ptr, (uint32_t)(grad->pitch_bytes / 4),
                            h->stream),
            "Kernel launch failed (kernel_sobel_gradients)");
+  h->launches += 1;
   return DFK_OK;
 }
 
@@ -622,6 +704,7 @@ DfkStatus dfk_gaussian_blur_down(DfkHandle h, const DfkImage* in, const DfkImage
   DFK_CUDA(h, launch_blur_down((int)in->width, (int)in->height, view_of(in), (int)out->width, (int)out->height,
                                (float*)out->ptr, (uint32_t)(out->pitch_bytes / 4), h->stream),
            "Kernel launch failed (kernel_gaussian_blur_down)");
+  h->launches += 1;
   return DFK_OK;
 }
 

@@ -33,14 +33,18 @@ struct Warped {
 };
 
 // q = (x,y,z,w) unit quaternion, t translation.  Exact-order restatement, see header comment.
-__device__ __forceinline__ Warped warp_pixel(float xf, float yf, float d, const float* __restrict__ q,
-                                             const float* __restrict__ t, float fx, float fy, float u0, float v0,
-                                             float border, float ulim, float vlim, float min_dpt)
+// Reproject's normalised ray coordinate (pinhole_camera_impl.h:54): (p - c) / f, IEEE division.
+// It depends only on the column (row), so kernels may tabulate it per item.
+__device__ __forceinline__ float ray_coord(float pf, float c, float f) { return __fdiv_rn(__fsub_rn(pf, c), f); }
+
+__device__ __forceinline__ Warped warp_ray(float xn, float yn, float d, const float* __restrict__ q,
+                                           const float* __restrict__ t, float fx, float fy, float u0, float v0,
+                                           float border, float ulim, float vlim, float min_dpt)
 {
   Warped w;
   // Reproject: PointT point((px - u0)/fx, (py - v0)/fy, 1); return point * depth;
-  w.xn = __fdiv_rn(__fsub_rn(xf, u0), fx);
-  w.yn = __fdiv_rn(__fsub_rn(yf, v0), fy);
+  w.xn = xn;
+  w.yn = yn;
   const float X0 = __fmul_rn(w.xn, d), X1 = __fmul_rn(w.yn, d), X2 = d;
   // Eigen QuaternionBase::_transformVector: uv = q.vec x v; uv += uv; v + w*uv + q.vec x uv
   float uv0 = __fsub_rn(__fmul_rn(q[1], X2), __fmul_rn(q[2], X1));
@@ -123,18 +127,40 @@ __device__ __forceinline__ void sample_grad(const float* __restrict__ grad, uint
   gy = lerp2(g00.y, g01.y, g10.y, g11.y, fu, fv);
 }
 
+__device__ __forceinline__ Warped warp_pixel(float xf, float yf, float d, const float* __restrict__ q,
+                                             const float* __restrict__ t, float fx, float fy, float u0, float v0,
+                                             float border, float ulim, float vlim, float min_dpt)
+{
+  return warp_ray(ray_coord(xf, u0, fx), ray_coord(yf, v0, fy), d, q, t, fx, fy, u0, v0, border, ulim, vlim, min_dpt);
+}
+
+// MUFU approximations (1-2 ulp) for everything downstream of the validity decision; the reference's
+// own GPU build uses --use_fast_math for all of it (sources/cuda/CMakeLists.txt:6)
+__device__ __forceinline__ float fast_rcp(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // m_estimators.h:50-56
 __device__ __forceinline__ float huber_weight(float x, float delta)
 {
   const float aa = fabsf(x);
-  return aa <= delta ? 1.0f : sqrtf(delta * (2.0f * aa - delta)) / aa;
+  return aa <= delta ? 1.0f : fast_sqrt(delta * (2.0f * aa - delta)) * fast_rcp(aa);
 }
 
 // a[k] = -(gx*A0[k] + gy*A1[k]),  A = dCam * [I | -hat(R pt)]   (warping.h:156-164,247-257)
 __device__ __forceinline__ void pose_jacobian_row(const Warped& w, float fx, float fy, float gx, float gy,
                                                   float (&a)[6], float& c00, float& c02, float& c11, float& c12)
 {
-  const float iz = 1.0f / w.tz;
+  const float iz = fast_rcp(w.tz);
   c00 = fx * iz;
   c11 = fy * iz;
   c02 = -(fx * w.tx) * iz * iz;
@@ -156,8 +182,9 @@ __device__ __forceinline__ float prx_jacobian(const Warped& w, const float* __re
   const float q2 = R[6] * w.xn + R[7] * w.yn + R[8];
   const float pJx = c00 * q0 + c02 * q2;
   const float pJy = c11 * q1 + c12 * q2;
-  const float prx = avg_dpt / (avg_dpt + d);
-  const float dJ = -avg_dpt / (prx * prx);
+  // DepthJacobianPrx: prx = avg/(avg+d); -avg/prx^2 == -(avg+d)^2/avg
+  const float s = avg_dpt + d;
+  const float dJ = -(s * s) * fast_rcp(avg_dpt);
   return -(gx * pJx + gy * pJy) * dJ;
 }
 

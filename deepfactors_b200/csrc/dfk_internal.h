@@ -75,7 +75,8 @@ struct SfmLaunchPlan {
 
 // dfk_sfm_fp32.cu
 cudaError_t launch_sfm_fp32(int code_size, const SfmItemDev* items_dev, const SfmLaunchPlan& plan,
-                            float* partials_dev, float* records_dev, cudaStream_t stream);
+                            float* partials_dev, float* records_dev, cudaStream_t stream,
+                            cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr);
 size_t sfm_partial_floats(int code_size);
 bool sfm_fp32_supported(int code_size);
 int sfm_max_ctas();  // grid size of the persistent kernel on the current device

@@ -33,10 +33,10 @@ namespace dfk {
 namespace {
 
 constexpr int kStages = 3;
-constexpr int kFeWarps = 4;
+constexpr int kFeWarps = 8;
 constexpr int kFeThreads = kFeWarps * 32;
-constexpr int kPxPerFeThread = kTilePixels / kFeThreads;  // 2
-static_assert(kTilePixels % kFeThreads == 0, "tile must be a multiple of the front-end width");
+static_assert(kTilePixels == kFeThreads, "one front-end thread per tile pixel");
+constexpr int kMaxTab = 1024;  // per-item tables of the normalised ray coordinates (columns / rows)
 
 struct TileMeta {
   int nvalid;
@@ -68,12 +68,14 @@ struct Smem {
   alignas(16) float img0[kStages][kTilePixels];
   alignas(16) float dpt0[kStages][kTilePixels];
   alignas(16) float M[2][Cfg::NFP * kTilePixels];
+  float xn_tab[kMaxTab];  // (x - u0) / fx, IEEE, per column of the current item
+  float yn_tab[kMaxTab];  // (y - v0) / fy per row
   alignas(8) uint64_t full_tma[kStages];
   uint64_t m_full[2];
   uint64_t m_empty[2];
   TileMeta meta[2];
   ItemSmem item;
-  int cnt[kPxPerFeThread * kFeWarps];  // valid counts per (round, warp)
+  int cnt[kFeWarps];  // valid counts per front-end warp
 };
 
 // reduce-scatter of 64 per-lane accumulators: afterwards lane l holds the warp-wide sums of
@@ -220,6 +222,14 @@ sfm_step_fp32_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
         named_bar_sync(1, kFeThreads);  // everyone finished reading the previous item's params
         load_item(sm.item, items[it], tid, kFeThreads, cta);
         cur_item = it;
+        {
+          // normalised ray tables (Reproject's IEEE divisions hoisted out of the pixel loop)
+          const SfmItemDev& src = items[it];
+          if (src.width <= kMaxTab && src.height <= kMaxTab) {
+            for (uint32_t x = tid; x < src.width; x += kFeThreads) sm.xn_tab[x] = ray_coord((float)x, src.u0, src.fx);
+            for (uint32_t y = tid; y < src.height; y += kFeThreads) sm.yn_tab[y] = ray_coord((float)y, src.v0, src.fy);
+          }
+        }
         named_bar_sync(1, kFeThreads);
       }
       const ItemSmem& I = sm.item;
@@ -236,104 +246,87 @@ sfm_step_fp32_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
         named_bar_sync(1, kFeThreads);
       }
 
-      // ---- geometry for this thread's pixels ------------------------------------------------
-      float feat[kPxPerFeThread][8];  // s, wa0..5, wr
-      bool ok[kPxPerFeThread];
+      // ---- geometry for this thread's pixel --------------------------------------------------
+      float feat[8];  // s, wa0..5, wr
+      bool ok = false;
+      const uint32_t s = tid;
+      if (s < n) {
+        const uint32_t p = p0 + s;
+        const uint32_t y = p / I.width, x = p - y * I.width;
+        const float d = sm.dpt0[st][s];
+        const bool tab = (I.width <= kMaxTab) && (I.height <= kMaxTab);
+        const float xn = tab ? sm.xn_tab[x] : ray_coord((float)x, I.u0, I.fx);
+        const float yn = tab ? sm.yn_tab[y] : ray_coord((float)y, I.v0, I.fy);
+        const Warped w = warp_ray(xn, yn, d, I.q, I.t, I.fx, I.fy, I.u0, I.v0, I.border, I.ulim, I.vlim, I.min_dpt);
+        if (w.valid) {
+          ok = true;
+          I.valid0[(size_t)y * I.valid0_pitch + x] = 1.0f;  // dense_sfm.h:161
+          int ix, iy;
+          float fu, fv, gx, gy;
+          bilin_setup(w.u, w.v, ix, iy, fu, fv);
+          sample_grad(I.grad1, I.grad1_pitch, (I.flags & ITEM_FLAG_GRAD_ALIGNED) != 0, ix, iy, fu, fv, gx, gy);
+          const float i1 = sample_scalar(I.img1, I.img1_pitch, ix, iy, fu, fv);
+          float a[6], c00, c02, c11, c12;
+          pose_jacobian_row(w, I.fx, I.fy, gx, gy, a, c00, c02, c11, c12);
+          const float e = prx_jacobian(w, I.R, d, I.avg_dpt, gx, gy, c00, c02, c11, c12);
+          const float diff = sm.img0[st][s] - i1;
+          const float hw = huber_weight(diff, I.huber_delta);
+          feat[0] = hw * e;
 #pragma unroll
-      for (int r = 0; r < kPxPerFeThread; ++r) {
-        const uint32_t s = r * kFeThreads + tid;
-        ok[r] = false;
-        if (s < n) {
-          const uint32_t p = p0 + s;
-          const uint32_t y = p / I.width, x = p - y * I.width;
-          const float d = sm.dpt0[st][s];
-          const Warped w = warp_pixel((float)x, (float)y, d, I.q, I.t, I.fx, I.fy, I.u0, I.v0, I.border, I.ulim,
-                                      I.vlim, I.min_dpt);
-          if (w.valid) {
-            ok[r] = true;
-            I.valid0[(size_t)y * I.valid0_pitch + x] = 1.0f;  // dense_sfm.h:161
-            int ix, iy;
-            float fu, fv, gx, gy;
-            bilin_setup(w.u, w.v, ix, iy, fu, fv);
-            sample_grad(I.grad1, I.grad1_pitch, (I.flags & ITEM_FLAG_GRAD_ALIGNED) != 0, ix, iy, fu, fv, gx, gy);
-            const float i1 = sample_scalar(I.img1, I.img1_pitch, ix, iy, fu, fv);
-            float a[6], c00, c02, c11, c12;
-            pose_jacobian_row(w, I.fx, I.fy, gx, gy, a, c00, c02, c11, c12);
-            const float e = prx_jacobian(w, I.R, d, I.avg_dpt, gx, gy, c00, c02, c11, c12);
-            const float diff = sm.img0[st][s] - i1;
-            const float hw = huber_weight(diff, I.huber_delta);
-            feat[r][0] = hw * e;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) feat[r][1 + j] = hw * a[j];
-            feat[r][7] = hw * diff;
-          }
+          for (int j = 0; j < 6; ++j) feat[1 + j] = hw * a[j];
+          feat[7] = hw * diff;
         }
       }
 
       // ---- compaction: valid pixels first --------------------------------------------------
-      int rank[kPxPerFeThread];
-#pragma unroll
-      for (int r = 0; r < kPxPerFeThread; ++r) {
-        const unsigned m = __ballot_sync(0xffffffffu, ok[r]);
-        const int before = __popc(m & ((1u << lane) - 1u));
-        rank[r] = ok[r] ? before : (lane - before);  // rank among valid / among invalid of this (round, warp)
-        if (lane == 0) sm.cnt[r * kFeWarps + warp] = __popc(m);
-      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      const int before = __popc(bal & ((1u << lane) - 1u));
+      const int rank = ok ? before : (lane - before);  // rank among the valid / invalid lanes of this warp
+      if (lane == 0) sm.cnt[warp] = __popc(bal);
       // the M buffer we are about to overwrite must have been drained by the Gram warps
       mbar_wait(&sm.m_empty[buf], ((i >> 1) & 1u) ^ 1u);
       named_bar_sync(1, kFeThreads);
-      int nvalid = 0, base_valid[kPxPerFeThread], base_invalid[kPxPerFeThread];
-      {
-        int vb = 0, ib = 0;
+      int nvalid = 0, base_valid = 0, base_invalid = 0;
 #pragma unroll
-        for (int r = 0; r < kPxPerFeThread; ++r)
-#pragma unroll
-          for (int w2 = 0; w2 < kFeWarps; ++w2) {
-            const int cvalid = sm.cnt[r * kFeWarps + w2];
-            if (w2 == warp) {
-              base_valid[r] = vb;
-              base_invalid[r] = ib;
-            }
-            vb += cvalid;
-            ib += 32 - cvalid;
-          }
-        nvalid = vb;
+      for (int w2 = 0; w2 < kFeWarps; ++w2) {
+        const int cvalid = sm.cnt[w2];
+        if (w2 == warp) {
+          base_valid = nvalid;
+          base_invalid = 32 * w2 - nvalid;
+        }
+        nvalid += cvalid;
       }
       const int padded = (nvalid + 31) & ~31;
       float* Mb = sm.M[buf];
+      if (ok) {
+        const int idx = base_valid + rank;
+        const float sc = feat[0];
+        if constexpr (C % 4 == 0 && C >= 4) {
+          constexpr int NV = C / 4;
+          const int rot = (NV >= 8) ? lane : (lane / (8 / (NV < 8 ? NV : 8)));
+          const float4* src = reinterpret_cast<const float4*>(&sm.jc[st][s * C]);
 #pragma unroll
-      for (int r = 0; r < kPxPerFeThread; ++r) {
-        if (ok[r]) {
-          const int idx = base_valid[r] + rank[r];
-          const uint32_t s = r * kFeThreads + tid;
-          const float sc = feat[r][0];
-          if constexpr (C % 4 == 0 && C >= 4) {
-            constexpr int NV = C / 4;
-            const int rot = (NV >= 8) ? lane : (lane / (8 / (NV < 8 ? NV : 8)));
-            const float4* src = reinterpret_cast<const float4*>(&sm.jc[st][s * C]);
-#pragma unroll
-            for (int k4 = 0; k4 < NV; ++k4) {
-              const int kk4 = (k4 + rot) % NV;
-              const float4 v = src[kk4];
-              Mb[(kk4 * 4 + 0) * kTilePixels + idx] = sc * v.x;
-              Mb[(kk4 * 4 + 1) * kTilePixels + idx] = sc * v.y;
-              Mb[(kk4 * 4 + 2) * kTilePixels + idx] = sc * v.z;
-              Mb[(kk4 * 4 + 3) * kTilePixels + idx] = sc * v.w;
-            }
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < C; ++kk) Mb[kk * kTilePixels + idx] = sc * sm.jc[st][s * C + kk];
+          for (int k4 = 0; k4 < NV; ++k4) {
+            const int kk4 = (k4 + rot) % NV;
+            const float4 v = src[kk4];
+            Mb[(kk4 * 4 + 0) * kTilePixels + idx] = sc * v.x;
+            Mb[(kk4 * 4 + 1) * kTilePixels + idx] = sc * v.y;
+            Mb[(kk4 * 4 + 2) * kTilePixels + idx] = sc * v.z;
+            Mb[(kk4 * 4 + 3) * kTilePixels + idx] = sc * v.w;
           }
-#pragma unroll
-          for (int j = 0; j < 7; ++j) Mb[(C + j) * kTilePixels + idx] = feat[r][1 + j];
-#pragma unroll
-          for (int j = C + 7; j < NFP; ++j) Mb[j * kTilePixels + idx] = 0.0f;
         } else {
-          const int idx = nvalid + base_invalid[r] + rank[r];
-          if (idx < padded) {
 #pragma unroll
-            for (int j = 0; j < NFP; ++j) Mb[j * kTilePixels + idx] = 0.0f;
-          }
+          for (int kk = 0; kk < C; ++kk) Mb[kk * kTilePixels + idx] = sc * sm.jc[st][s * C + kk];
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) Mb[(C + j) * kTilePixels + idx] = feat[1 + j];
+#pragma unroll
+        for (int j = C + 7; j < NFP; ++j) Mb[j * kTilePixels + idx] = 0.0f;
+      } else {
+        const int idx = nvalid + base_invalid + rank;
+        if (idx < padded) {
+#pragma unroll
+          for (int j = 0; j < NFP; ++j) Mb[j * kTilePixels + idx] = 0.0f;
         }
       }
       if (tid == 0) {
@@ -388,24 +381,24 @@ sfm_step_fp32_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
         cur_slot = meta.slot;
       }
       inliers += (unsigned)meta.nvalid;
-      const float* Mr = sm.M[buf] + (8 * bi) * kTilePixels + lane;
-      const float* Mc = sm.M[buf] + (8 * bj) * kTilePixels + lane;
+      // 32-bit shared-window addresses + explicit ld.shared keep the loop at 64 accumulators + 12 operands
+      const uint32_t mr = smem_u32(sm.M[buf]) + 4u * ((8 * bi) * kTilePixels + lane);
+      const uint32_t mc = smem_u32(sm.M[buf]) + 4u * ((8 * bj) * kTilePixels + lane);
       const int steps = (meta.nvalid + 31) >> 5;
       for (int s = 0; s < steps; ++s) {
-        float r[8], c[8];
+        float r[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = Mr[j * kTilePixels + s * 32];
-        if (bi == bj) {
+        for (int j = 0; j < 8; ++j) r[j] = lds_f32(mr + 4u * (j * kTilePixels + s * 32));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) c[j] = r[j];
-        } else {
+        for (int h = 0; h < 2; ++h) {
+          float c[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) c[j] = Mc[j * kTilePixels + s * 32];
+          for (int k = 0; k < 4; ++k) c[k] = (bi == bj) ? r[4 * h + k] : lds_f32(mc + 4u * ((4 * h + k) * kTilePixels + s * 32));
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[j * 8 + 4 * h + k] = fmaf(r[j], c[k], acc[j * 8 + 4 * h + k]);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[j * 8 + k] = fmaf(r[j], c[k], acc[j * 8 + k]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.m_empty[buf]);
@@ -554,7 +547,7 @@ sfm_finalize_kernel(const SfmItemDev* __restrict__ items, const float* __restric
 
 template <int C>
 cudaError_t launch_impl(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, float* partials_dev,
-                        float* records_dev, cudaStream_t stream)
+                        float* records_dev, cudaStream_t stream, cudaEvent_t ev_start, cudaEvent_t ev_stop)
 {
   using Cfg = SfmCfg<C>;
   const size_t smem = sizeof(Smem<C>);
@@ -562,8 +555,10 @@ cudaError_t launch_impl(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, 
                                          (int)smem);
   if (err != cudaSuccess) return err;
   const int threads = (kFeWarps + Cfg::NBLK) * 32;
+  if (ev_start) cudaEventRecord(ev_start, stream);
   sfm_step_fp32_kernel<C><<<plan.num_ctas, threads, smem, stream>>>(items_dev, plan.num_items, plan.num_tiles,
                                                                     partials_dev);
+  if (ev_stop) cudaEventRecord(ev_stop, stream);
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
   dim3 grid(plan.num_items, C + 1);
@@ -594,12 +589,13 @@ int sfm_max_ctas()
 }
 
 cudaError_t launch_sfm_fp32(int code_size, const SfmItemDev* items_dev, const SfmLaunchPlan& plan,
-                            float* partials_dev, float* records_dev, cudaStream_t stream)
+                            float* partials_dev, float* records_dev, cudaStream_t stream, cudaEvent_t ev_start,
+                            cudaEvent_t ev_stop)
 {
   switch (code_size) {
-    case 8: return launch_impl<8>(items_dev, plan, partials_dev, records_dev, stream);
-    case 16: return launch_impl<16>(items_dev, plan, partials_dev, records_dev, stream);
-    case 32: return launch_impl<32>(items_dev, plan, partials_dev, records_dev, stream);
+    case 8: return launch_impl<8>(items_dev, plan, partials_dev, records_dev, stream, ev_start, ev_stop);
+    case 16: return launch_impl<16>(items_dev, plan, partials_dev, records_dev, stream, ev_start, ev_stop);
+    case 32: return launch_impl<32>(items_dev, plan, partials_dev, records_dev, stream, ev_start, ev_stop);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -102,9 +102,11 @@ typedef enum { DFK_GRAM_AUTO = 0, DFK_GRAM_FP32 = 1, DFK_GRAM_TF32X3 = 2 } DfkGr
  * device < 0 => current device. */
 DfkStatus dfk_create(int device, DfkHandle* out);
 DfkStatus dfk_destroy(DfkHandle h);
-/* cudaStream_t to launch on (NULL = the handle's own stream).  The reference uses the
- * default stream + cudaDeviceSynchronize (launch_utils.h:28). */
+/* cudaStream_t to launch on; NULL is the legacy default stream (the one the reference uses,
+ * with cudaDeviceSynchronize after every launch: launch_utils.h:28).  A new handle launches on a
+ * private non-blocking stream; dfk_use_own_stream returns to it. */
 DfkStatus dfk_set_stream(DfkHandle h, void* cuda_stream);
+DfkStatus dfk_use_own_stream(DfkHandle h);
 void* dfk_get_stream(DfkHandle h);
 DfkStatus dfk_synchronize(DfkHandle h);
 const char* dfk_last_error(DfkHandle h);
@@ -112,6 +114,16 @@ const char* dfk_status_string(DfkStatus s);
 int dfk_version(void);
 /* 1 if this build has a RunStep kernel for the code size (reference: only 32, cu_sfmaligner.cpp:209) */
 int dfk_sfm_supports_code_size(int code_size);
+
+/* Measurement hooks (no reference equivalent; the reference times with std::clock around
+ * synchronous calls, sources/common/timing.h:28-45).  With profiling on, every launch of the
+ * dominant kernel (the per-tile warp+Gram kernel of RunStep) is bracketed by CUDA events on the
+ * launching stream.  dfk_get_profile synchronizes the stream, returns the summed device time
+ * of those launches and their count plus the number of ALL kernels this handle launched since the
+ * last call, and resets the counters. */
+DfkStatus dfk_set_profiling(DfkHandle h, int enabled);
+DfkStatus dfk_get_profile(DfkHandle h, double* main_kernel_ms, uint64_t* main_kernel_launches,
+                          uint64_t* total_kernel_launches);
 
 /* SfmAligner ctor params + SetEvalThreadsBlocks/SetStepThreadsBlocks (cu_sfmaligner.cpp:187-203) */
 DfkStatus dfk_sfm_set_params(DfkHandle h, const DfkSfmAlignerParams* p);

@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 
 from deepfactors_b200 import se3, synth
+from helpers import scenenet_inputs
 
 
 # ------------------------------------------------------------------------------------------ helpers
@@ -299,14 +300,6 @@ def test_evaluate_error_uses_border_one_and_matches_step_residual_semantics(orac
 
 
 # ------------------------------------------------------------------------------------------ SE3 KAT
-def scenenet_inputs(golden):
-    img0 = golden["blur25_1047"]
-    img1 = golden["blur25_1052"]
-    dpt0 = (golden["depth_1047_mm"].astype(np.float32) * np.float32(1 / 1000.0)).astype(np.float32)
-    cam = synth.Camera.scenenet(img0.shape[1], img0.shape[0])
-    return cam, img0, img1, dpt0
-
-
 def test_se3_image_alignment_converges_like_reference(oracle, golden):
     """tests/ut_se3aligner.cpp:173-211 ImageAlignmentTest: 40 GN iterations from identity, huber 0.1,
     error = residual / inliers <= 1e-3."""

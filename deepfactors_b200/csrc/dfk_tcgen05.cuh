@@ -1,0 +1,103 @@
+// dfk_tcgen05.cuh -- inline-PTX wrappers for the 5th-generation tensor-core path (sm_100a):
+// TMEM allocation, tcgen05.st / tcgen05.ld, tcgen05.mma kind::tf32 with A in TMEM and B in shared
+// memory, tcgen05.commit, the tcgen05 fences, and the descriptor encodings.
+// Field layouts follow the PTX ISA "tcgen05" chapter as restated in the vendored CUTLASS headers
+// (cute/arch/mma_sm100_desc.hpp, mma_sm100_umma.hpp, copy_sm100.hpp, tmem_allocator_sm100.hpp) --
+// read for the bit layouts only; no CUTLASS code is compiled into this library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dfk_async.cuh"
+
+namespace dfk {
+
+// ---------------------------------------------------------------------------------- TMEM allocation
+// one full warp; writes the base address (lane 0, column c) to *dst_smem.  ncols: power of two >= 32
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
+{
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish()
+{
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------- fences
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma reading B through a descriptor)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------- TMEM <-> registers
+// 32x32b shape: thread i of the warp accesses lane (quarter_base + i), `n` consecutive 32-bit columns.
+// taddr = tmem_base + (lane_base << 16) + column, lane_base = 32 * (warp_id % 4).
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&v)[8])
+{
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v)
+{
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------- descriptors
+// Instruction descriptor, kind::tf32, fp32 accumulate, A and B K-major, dense:
+//   [4,6) c_format = 1 (F32) | [7,10) a_format = 2 (TF32) | [10,13) b_format = 2 (TF32)
+//   [15] a_major = 0 | [16] b_major = 0 | [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N)
+{
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Shared-memory matrix descriptor, K-major operand, no swizzle ("interleave"): the operand is a grid of
+// 8-row x 16-byte core matrices stored as 128 contiguous bytes; `lbo` = byte distance between core
+// matrices adjacent in K, `sbo` = byte distance between core matrices adjacent in M/N.
+//   [0,14) addr >> 4 | [16,30) lbo >> 4 | [32,46) sbo >> 4 | [46,48) version = 1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_smem_desc_kmajor_noswizzle(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
+{
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+// ---------------------------------------------------------------------------------- MMA + commit
+// D[tmem] (+)= A[tmem] * B[smem]^T ; one elected thread issues.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             bool accumulate)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
+// arrives (count 1) on `bar` when every tcgen05 operation this thread issued so far has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+}  // namespace dfk

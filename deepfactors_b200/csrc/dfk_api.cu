@@ -37,6 +37,8 @@ struct DfkContext {
   size_t items_cap = 0;
   float* partials_dev = nullptr;
   size_t partials_cap = 0;  // floats
+  float* ray_tabs_dev = nullptr;
+  size_t ray_tabs_cap = 0;  // floats
   float* records_dev = nullptr;
   size_t records_cap = 0;  // floats
   float* records_host = nullptr;  // pinned
@@ -218,8 +220,10 @@ cudaError_t ensure(T** ptr, size_t* cap, size_t need)
   return e;
 }
 
-DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, SfmLaunchPlan* plan)
+DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, int tile_px, int max_ctas,
+                      float* ray_tabs, SfmLaunchPlan* plan)
 {
+  size_t ray_cursor = 0;
   const DfkDenseSfmParams& sp = h->params.sfmparams;
   h->items_host.resize(n);
   uint32_t tile_cursor = 0;
@@ -249,7 +253,9 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
     d.dpt0_pitch = (uint32_t)(w.dpt0.pitch_bytes / 4); d.valid0_pitch = (uint32_t)(w.valid0.pitch_bytes / 4);
     d.jac_pitch = (uint32_t)(w.prx0_jac.pitch_bytes / 4); d.grad1_pitch = (uint32_t)(w.grad1.pitch_bytes / 4);
     d.width = W; d.height = H; d.num_pixels = W * H;
-    d.num_tiles = (d.num_pixels + kTilePixels - 1) / kTilePixels;
+    d.num_tiles = (d.num_pixels + tile_px - 1) / tile_px;
+    d.ray_tab = ray_tabs ? ray_tabs + ray_cursor : nullptr;
+    ray_cursor += (size_t)W + H;
     d.tile_begin = tile_cursor;
     tile_cursor += d.num_tiles;
     d.perm_mul = perm_multiplier(d.num_tiles);
@@ -261,7 +267,7 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
     if (aligned(d.grad1, 8) && d.grad1_pitch % 2 == 0) d.flags |= ITEM_FLAG_GRAD_ALIGNED;
   }
   const int T = (int)tile_cursor;
-  int G = std::min(h->num_sms, T);
+  int G = std::min(max_ctas, T);
   if (G < 1) G = 1;
   plan->num_items = n;
   plan->num_tiles = T;
@@ -328,14 +334,24 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
   if (!sfm_fp32_supported(code_size))
     return fail(h, DFK_ERR_UNSUPPORTED,
                 "[SfmAligner::RunStep] no kernel instantiated for code size " + std::to_string(code_size));
-  if (h->gram_mode == DFK_GRAM_TF32X3)
-    return fail(h, DFK_ERR_UNSUPPORTED, "[SfmAligner::RunStep] tensor-core Gram path not available in this build");
+  const bool tc = (h->gram_mode == DFK_GRAM_TF32X3) || (h->gram_mode == DFK_GRAM_AUTO && sfm_tc_supported(code_size));
+  if (tc && !sfm_tc_supported(code_size))
+    return fail(h, DFK_ERR_UNSUPPORTED,
+                "[SfmAligner::RunStep] tensor-core Gram path is not instantiated for code size " +
+                    std::to_string(code_size));
   DeviceGuard guard(h->device);
   SfmLaunchPlan plan;
-  DfkStatus st = build_items(h, items, n, code_size, &plan);
+  if (tc) {
+    size_t ray_floats = 0;
+    for (int i = 0; i < n; ++i) ray_floats += (size_t)items[i].img0.width + items[i].img0.height;
+    DFK_CUDA(h, ensure(&h->ray_tabs_dev, &h->ray_tabs_cap, ray_floats), "[SfmAligner::RunStep] scratch allocation failed");
+  }
+  DfkStatus st = build_items(h, items, n, code_size, tc ? kTcTilePixels : kTilePixels, tc ? 2 * h->num_sms : h->num_sms,
+                             tc ? h->ray_tabs_dev : nullptr, &plan);
   if (st != DFK_OK) return st;
+  const size_t pfloats = tc ? (size_t)kTcPartialFloats : sfm_partial_floats(code_size);
   DFK_CUDA(h, ensure(&h->items_dev, &h->items_cap, (size_t)n), "[SfmAligner::RunStep] scratch allocation failed");
-  DFK_CUDA(h, ensure(&h->partials_dev, &h->partials_cap, (size_t)plan.num_partials * sfm_partial_floats(code_size)),
+  DFK_CUDA(h, ensure(&h->partials_dev, &h->partials_cap, (size_t)plan.num_partials * pfloats),
            "[SfmAligner::RunStep] scratch allocation failed");
   DFK_CUDA(h, cudaMemcpyAsync(h->items_dev, h->items_host.data(), sizeof(SfmItemDev) * n, cudaMemcpyHostToDevice,
                               h->stream),
@@ -345,7 +361,15 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     DfkStatus ps = profile_events(h, &ev0, &ev1);
     if (ps != DFK_OK) return ps;
   }
-  DFK_CUDA(h, launch_sfm_fp32(code_size, h->items_dev, plan, h->partials_dev, records_dev, h->stream, ev0, ev1),
+  if (tc) {
+    DFK_CUDA(h, launch_sfm_tc(h->items_dev, plan, h->ray_tabs_dev, h->partials_dev, h->stream, ev0, ev1),
+             "[SfmAligner::RunStep] kernel launch failed");
+    h->launches += 1;  // ray-table kernel
+  } else {
+    DFK_CUDA(h, launch_sfm_fp32(code_size, h->items_dev, plan, h->partials_dev, records_dev, h->stream, ev0, ev1),
+             "[SfmAligner::RunStep] kernel launch failed");
+  }
+  DFK_CUDA(h, launch_sfm_finalize(code_size, tc, h->items_dev, n, h->partials_dev, records_dev, h->stream),
            "[SfmAligner::RunStep] kernel launch failed");
   h->launches += 2;  // step kernel + finalize kernel
   return DFK_OK;
@@ -413,7 +437,7 @@ DfkStatus dfk_destroy(DfkHandle h)
   DeviceGuard guard(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   cudaFree(h->simple_scratch); cudaFree(h->counter); cudaFree(h->out_dev); cudaFree(h->code_dev);
-  cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev);
+  cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev); cudaFree(h->ray_tabs_dev);
   if (h->out_host) cudaFreeHost(h->out_host);
   if (h->records_host) cudaFreeHost(h->records_host);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);

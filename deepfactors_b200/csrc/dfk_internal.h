@@ -46,6 +46,8 @@ struct SfmItemDev {
   // partial_begin + (c - first_cta)
   uint32_t first_cta, num_ctas, partial_begin;
   uint32_t flags;  // bit0: bulk-copy (TMA) eligible, bit1: grad1 rows are 8-byte aligned
+  // normalised ray tables in device scratch: xn[0..width), then yn[0..height) (tensor-core kernel)
+  const float* ray_tab;
   // relative-pose Jacobians (warping.h:120-134), row-major 6x6; used by the finalize kernel
   float P0[36];
   float P1[36];
@@ -63,7 +65,13 @@ struct SfmCfg {
   static constexpr int PARTIAL_FLOATS = NFP * NFP + 8;  // G (row major NFP x NFP) | inliers(u32) | pad
 };
 
-constexpr int kTilePixels = 256;
+constexpr int kTilePixels = 256;    // fp32 kernel
+constexpr int kTcTilePixels = 128;  // tensor-core kernel
+// tensor-core partial: rows = TMEM lanes that carry data (32 code-h, 32 code-l, 7 pose-h, 7 pose-l),
+// columns = B features (32 code, 7 pose/residual, 1 pad)
+constexpr int kTcRows = 78;
+constexpr int kTcCols = 40;
+constexpr int kTcPartialFloats = kTcRows * kTcCols + 8;
 
 struct SfmLaunchPlan {
   int num_items = 0;
@@ -77,6 +85,13 @@ struct SfmLaunchPlan {
 cudaError_t launch_sfm_fp32(int code_size, const SfmItemDev* items_dev, const SfmLaunchPlan& plan,
                             float* partials_dev, float* records_dev, cudaStream_t stream,
                             cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr);
+cudaError_t launch_sfm_finalize(int code_size, bool tc, const SfmItemDev* items_dev, int num_items,
+                                const float* partials_dev, float* records_dev, cudaStream_t stream);
+// dfk_sfm_tc.cu
+bool sfm_tc_supported(int code_size);
+cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, float* ray_tabs_dev,
+                          float* partials_dev, cudaStream_t stream, cudaEvent_t ev_start = nullptr,
+                          cudaEvent_t ev_stop = nullptr);
 size_t sfm_partial_floats(int code_size);
 bool sfm_fp32_supported(int code_size);
 int sfm_max_ctas();  // grid size of the persistent kernel on the current device

@@ -1,0 +1,580 @@
+// dfk_sfm_tc.cu -- SfmAligner::RunStep hot path, tcgen05 tensor-core Gram variant (sm_100a, C = 32).
+//
+// Same contract as dfk_sfm_fp32.cu (replaces kernel_step_calculate + DenseSfm + the two-kernel
+// reduction of sources/cuda/cu_sfmaligner.cpp:40-70,149-185, dense_sfm.h:133-201), different engine
+// for the reduced Gram  G = sum_p m_p^T m_p,  m = w*[ e*jc (32) | a (6) | diff (1) ]  (39 features):
+//
+//   Split precision ("3xTF32" folded into ONE MMA): every feature value v is split exactly into
+//   h = the bits the tensor core keeps (fp32 -> tf32 is a truncation of the low 13 mantissa bits on
+//   this hardware, measured by tools/umma_probe.cu) and l = v - h.  With A = [h rows ; l rows] (78 of
+//   M = 128 rows) and B = h (39 of N = 48 columns), one tcgen05.mma.kind::tf32 per 8 pixels yields
+//   HH = sum h h^T and LH = sum l h^T;  G = HH + LH + LH^T  drops only the l*l terms (~2^-22).
+//
+//   Per CTA (256 threads, 2 CTAs / SM, 256 TMEM columns each):
+//     warps 4-7  front-end : one thread per pixel of a 128-pixel tile: exact-order validity chain, bilinear
+//                            gathers, Jacobian row, Huber; valid pixels compacted; per-pixel scalars
+//                            (s = w*e, w*a[6], w*diff) + the pixel's slot id go to shared memory.
+//     warps 0-2  operand   : lane = feature row.  warp 0: h of the 32 code features (raw s*jc; the
+//                            tensor core truncates), also written K-major to shared memory as B;
+//                            warp 1: l of the code features; warp 2: h and l of the 7 pose/residual
+//                            features.  A goes registers -> TMEM with tcgen05.st (lane = row, column =
+//                            pixel); the code Jacobian rows come from the TMA-staged tile with one
+//                            conflict-free LDS per pixel (lane = code dimension).
+//     warp 3     control   : lane 0 issues the MMAs (A from TMEM, B from shared memory through a
+//                            K-major no-swizzle descriptor) and the tcgen05.commit arrivals.
+//   The fp32 accumulator in TMEM adds with truncation (measured: ~ -2^-24 relative per k-step), so a
+//   chain is cut every kFlushTiles tiles: the operand warps pull the finished chain out of TMEM
+//   (tcgen05.ld) and add it to register accumulators in round-to-nearest fp32.
+//
+// Tile staging (cp.async.bulk row segments into a 4-deep ring), the static tile->CTA assignment, the
+// in-item tile permutation, the per-CTA partials and the wide deterministic finalize are those of the
+// fp32 kernel.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dfk_async.cuh"
+#include "dfk_geom.cuh"
+#include "dfk_internal.h"
+#include "dfk_tcgen05.cuh"
+
+namespace dfk {
+
+namespace {
+
+constexpr int C = 32;
+constexpr int TILE = kTcTilePixels;  // 128
+constexpr int HALF = 64;
+constexpr int STAGES = 4;
+constexpr int FE_THREADS = 128;
+constexpr int THREADS = 256;
+constexpr int NB = 48;           // MMA N (39 used)
+constexpr int MM = 128;          // MMA M (78 used)
+constexpr int kFlushTiles = 8;   // TMEM accumulation chain length (tiles)
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t A_COL = 0;    // [0,128): two 64-column halves of A
+constexpr uint32_t D_COL = 128;  // [128,176), [176,224): two accumulators
+constexpr uint32_t B_SBO = (HALF / 4) * 128;                 // 2048 B between 8-row groups
+constexpr uint32_t B_HALF_BYTES = (NB / 8) * B_SBO;           // 12288 B
+constexpr int JC_STAGE_FLOATS = (TILE + 1) * C;               // +1: an all-zero row for padded pixels
+
+struct TileMeta {
+  int nvalid;
+  int item_changed;
+  int slot;
+  int pad;
+};
+
+struct ItemSmem {
+  float q[4];
+  float t[3];
+  float R[9];
+  float fx, fy, u0, v0, border, ulim, vlim, min_dpt, avg_dpt, huber_delta;
+  const float* img0;
+  const float* img1;
+  const float* dpt0;
+  float* valid0;
+  const float* jac;
+  const float* grad1;
+  const float* ray_tab;
+  uint32_t img0_pitch, img1_pitch, dpt0_pitch, valid0_pitch, jac_pitch, grad1_pitch;
+  uint32_t width, height, num_pixels, tile_begin, num_tiles, perm_mul, flags, slot;
+};
+
+struct Smem {
+  alignas(128) float jc[STAGES][JC_STAGE_FLOATS];
+  alignas(128) unsigned char B[2][B_HALF_BYTES];
+  alignas(16) float img0[STAGES][TILE];
+  alignas(16) float dpt0[STAGES][TILE];
+  alignas(16) float feat[2][8][TILE];  // K-major per-pixel scalars of the compacted pixels: s, wa0..5, wr
+  alignas(16) int sid[2][TILE];        // slot (row of the jc stage) of each compacted pixel
+  alignas(8) uint64_t tma_full[STAGES];
+  uint64_t feat_full[2];
+  uint64_t feat_empty[2];
+  uint64_t a_full[2];
+  uint64_t a_empty[2];
+  uint64_t d_full[2];
+  uint64_t d_empty[2];
+  TileMeta meta[2];
+  ItemSmem item;
+  int cnt[2][4];  // per feat buffer: a fast warp may start tile i+1 while a slow one still reads tile i's counts
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, int tid, int cta)
+{
+  if (tid < 4) dst.q[tid] = src.q[tid];
+  if (tid < 3) dst.t[tid] = src.t[tid];
+  if (tid < 9) dst.R[tid] = src.R[tid];
+  if (tid == 32) {
+    dst.fx = src.fx; dst.fy = src.fy; dst.u0 = src.u0; dst.v0 = src.v0;
+    dst.border = src.border; dst.ulim = src.ulim; dst.vlim = src.vlim;
+    dst.min_dpt = src.min_dpt; dst.avg_dpt = src.avg_dpt; dst.huber_delta = src.huber_delta;
+  }
+  if (tid == 64) {
+    dst.img0 = src.img0; dst.img1 = src.img1; dst.dpt0 = src.dpt0; dst.valid0 = src.valid0;
+    dst.jac = src.jac; dst.grad1 = src.grad1; dst.ray_tab = src.ray_tab;
+    dst.img0_pitch = src.img0_pitch; dst.img1_pitch = src.img1_pitch; dst.dpt0_pitch = src.dpt0_pitch;
+    dst.valid0_pitch = src.valid0_pitch; dst.jac_pitch = src.jac_pitch; dst.grad1_pitch = src.grad1_pitch;
+  }
+  if (tid == 96) {
+    dst.width = src.width; dst.height = src.height; dst.num_pixels = src.num_pixels;
+    dst.tile_begin = src.tile_begin; dst.num_tiles = src.num_tiles; dst.perm_mul = src.perm_mul;
+    dst.flags = src.flags;
+    dst.slot = src.partial_begin + (uint32_t)cta - src.first_cta;
+  }
+}
+
+__device__ __forceinline__ void issue_tile_loads(Smem& sm, const SfmItemDev* __restrict__ items, int it, int g, int st)
+{
+  const SfmItemDev& I = items[it];
+  const uint32_t k = (uint32_t)g - I.tile_begin;
+  const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
+  const uint32_t p0 = tau * TILE;
+  const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
+  const uint32_t W = I.width;
+  uint32_t y = p0 / W;
+  uint32_t x = p0 - y * W;
+  mbar_arrive_expect_tx(&sm.tma_full[st], n * (C + 2) * 4u);
+  uint32_t slot = 0;
+  while (slot < n) {
+    const uint32_t seg = min(W - x, n - slot);
+    bulk_g2s(&sm.jc[st][slot * C], I.jac + (size_t)y * I.jac_pitch + (size_t)x * C, seg * C * 4u, &sm.tma_full[st]);
+    bulk_g2s(&sm.img0[st][slot], I.img0 + (size_t)y * I.img0_pitch + x, seg * 4u, &sm.tma_full[st]);
+    bulk_g2s(&sm.dpt0[st][slot], I.dpt0 + (size_t)y * I.dpt0_pitch + x, seg * 4u, &sm.tma_full[st]);
+    slot += seg;
+    x = 0;
+    ++y;
+  }
+}
+
+__device__ __forceinline__ void coop_tile_loads(Smem& sm, const ItemSmem& I, uint32_t p0, uint32_t n, int st, int ft)
+{
+  const uint32_t W = I.width;
+  for (uint32_t s = ft; s < n; s += FE_THREADS) {
+    const uint32_t p = p0 + s;
+    const uint32_t y = p / W, x = p - y * W;
+    sm.img0[st][s] = __ldg(I.img0 + (size_t)y * I.img0_pitch + x);
+    sm.dpt0[st][s] = __ldg(I.dpt0 + (size_t)y * I.dpt0_pitch + x);
+  }
+  for (uint32_t e = ft; e < n * C; e += FE_THREADS) {
+    const uint32_t s = e / C, kk = e - s * C;
+    const uint32_t p = p0 + s;
+    const uint32_t y = p / W, x = p - y * W;
+    sm.jc[st][e] = __ldg(I.jac + (size_t)y * I.jac_pitch + (size_t)x * C + kk);
+  }
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t addr)
+{
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d)
+{
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+// chain bookkeeping shared (by construction) between the control thread and the operand warps
+struct ChainState {
+  int e = -1;              // current chain index
+  int tiles_in_chain = 0;
+  __device__ __forceinline__ bool starts_chain(int i, const TileMeta& m) const
+  {
+    return i == 0 || m.item_changed != 0 || tiles_in_chain == kFlushTiles;
+  }
+};
+
+__global__ void __launch_bounds__(THREADS, 2)
+sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_tiles, float* __restrict__ partials)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int G = gridDim.x;
+  const int g_lo = (int)(((long long)cta * num_tiles) / G);
+  const int g_hi = (int)(((long long)(cta + 1) * num_tiles) / G);
+  const int ntiles = g_hi - g_lo;
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&sm.tma_full[s], 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm.feat_full[b], FE_THREADS);
+      mbar_init(&sm.feat_empty[b], 3);
+      mbar_init(&sm.a_full[b], 3);
+      mbar_init(&sm.a_empty[b], 1);
+      mbar_init(&sm.d_full[b], 1);
+      mbar_init(&sm.d_empty[b], 3);
+    }
+    mbar_fence_init();
+  }
+  // zero row of every jc stage and the whole B buffer (rows 39..47 are never written again)
+  for (int s = 0; s < STAGES; ++s)
+    if (tid < C) sm.jc[s][TILE * C + tid] = 0.0f;
+  for (int e = tid; e < (int)(2 * B_HALF_BYTES / 4); e += THREADS) reinterpret_cast<float*>(sm.B)[e] = 0.0f;
+  if (warp == 3) {
+    tmem_alloc(&sm.tmem_base, TMEM_COLS);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = sm.tmem_base;
+
+  if (ntiles > 0) {
+    if (warp >= 4) {
+      // ======================================================================= front-end warps
+      const int ft = tid - 128;  // 0..127 = pixel slot
+      const int fwarp = warp - 4;
+      int it = 0;
+      while (it + 1 < num_items && (uint32_t)g_lo >= items[it].tile_begin + items[it].num_tiles) ++it;
+      int it_pf = it;
+      uint32_t tma_phase_bits = 0;
+      int cur_item = -1;
+      if (ft == 0) {
+        for (int j = 0; j < 2 && j < ntiles; ++j) {  // prefetch distance 2
+          const int g = g_lo + j;
+          while ((uint32_t)g >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
+          if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, g, j % STAGES);
+        }
+      }
+      for (int i = 0; i < ntiles; ++i) {
+        const int g = g_lo + i;
+        const int st = i % STAGES;
+        const int fb = i & 1;
+        while ((uint32_t)g >= items[it].tile_begin + items[it].num_tiles) ++it;
+        const bool changed = (it != cur_item);
+        if (changed) {
+          named_bar_sync(1, FE_THREADS);
+          load_item(sm.item, items[it], ft, cta);
+          cur_item = it;
+          named_bar_sync(1, FE_THREADS);
+        }
+        const ItemSmem& I = sm.item;
+        const uint32_t k = (uint32_t)g - I.tile_begin;
+        const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
+        const uint32_t p0 = tau * TILE;
+        const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
+        const bool bulk = (I.flags & ITEM_FLAG_BULK) != 0;
+        if (bulk) {
+          mbar_wait(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
+          tma_phase_bits ^= (1u << st);
+        } else {
+          // the stage was last read by the operand warps of tile i-4: released before feat_empty(i-2) was
+          coop_tile_loads(sm, I, p0, n, st, ft);
+          named_bar_sync(1, FE_THREADS);
+        }
+
+        float feat[8];
+        bool ok = false;
+        const uint32_t s = ft;
+        if (s < n) {
+          const uint32_t p = p0 + s;
+          const uint32_t y = p / I.width, x = p - y * I.width;
+          const float d = sm.dpt0[st][s];
+          const float xn = __ldg(I.ray_tab + x);
+          const float yn = __ldg(I.ray_tab + I.width + y);
+          const Warped w = warp_ray(xn, yn, d, I.q, I.t, I.fx, I.fy, I.u0, I.v0, I.border, I.ulim, I.vlim, I.min_dpt);
+          if (w.valid) {
+            ok = true;
+            I.valid0[(size_t)y * I.valid0_pitch + x] = 1.0f;  // dense_sfm.h:161
+            int ix, iy;
+            float fu, fv, gx, gy;
+            bilin_setup(w.u, w.v, ix, iy, fu, fv);
+            sample_grad(I.grad1, I.grad1_pitch, (I.flags & ITEM_FLAG_GRAD_ALIGNED) != 0, ix, iy, fu, fv, gx, gy);
+            const float i1 = sample_scalar(I.img1, I.img1_pitch, ix, iy, fu, fv);
+            float a[6], c00, c02, c11, c12;
+            pose_jacobian_row(w, I.fx, I.fy, gx, gy, a, c00, c02, c11, c12);
+            const float e = prx_jacobian(w, I.R, d, I.avg_dpt, gx, gy, c00, c02, c11, c12);
+            const float diff = sm.img0[st][s] - i1;
+            const float hw = huber_weight(diff, I.huber_delta);
+            feat[0] = hw * e;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) feat[1 + j] = hw * a[j];
+            feat[7] = hw * diff;
+          }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        const int rank = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) sm.cnt[fb][fwarp] = __popc(bal);
+        // feat[fb] / sid[fb] of tile i-2 must have been consumed; this also frees ring stage (i+2)%4
+        mbar_wait(&sm.feat_empty[fb], ((i >> 1) & 1u) ^ 1u);
+        named_bar_sync(1, FE_THREADS);
+        if (ft == 0) {
+          const int gn = g + 2;
+          if (gn < g_hi) {
+            while ((uint32_t)gn >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
+            if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, gn, (i + 2) % STAGES);
+          }
+        }
+        int nvalid = 0, base = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < 4; ++w2) {
+          if (w2 == fwarp) base = nvalid;
+          nvalid += sm.cnt[fb][w2];
+        }
+        if (ok) {
+          const int c = base + rank;
+          sm.sid[fb][c] = (int)s;
+#pragma unroll
+          for (int f = 0; f < 8; ++f) sm.feat[fb][f][c] = feat[f];
+        }
+        // pad the compacted list to a multiple of 8 with "pixels" that contribute exactly zero
+        if (ft < 8) {
+          const int c = nvalid + ft;
+          if (c < ((nvalid + 7) & ~7)) {
+            sm.sid[fb][c] = TILE;  // the all-zero jc row
+#pragma unroll
+            for (int f = 0; f < 8; ++f) sm.feat[fb][f][c] = 0.0f;
+          }
+        }
+        if (ft == 0) {
+          sm.meta[fb].nvalid = nvalid;
+          sm.meta[fb].item_changed = changed ? 1 : 0;
+          sm.meta[fb].slot = (int)I.slot;
+        }
+        mbar_arrive(&sm.feat_full[fb]);
+      }
+    } else if (warp == 3) {
+      // ======================================================================= control warp
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_tf32(MM, NB);
+        ChainState ch;
+        bool first = true;
+        for (int i = 0; i < ntiles; ++i) {
+          const int fb = i & 1;
+          TileMeta meta{};
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&sm.a_full[h], i & 1u);
+            tc_fence_after();
+            if (h == 0) {
+              meta = sm.meta[fb];
+              if (ch.starts_chain(i, meta)) {
+                if (i > 0) umma_commit(&sm.d_full[ch.e & 1]);
+                ch.e += 1;
+                ch.tiles_in_chain = 0;
+                first = true;
+                const int use = ch.e >> 1;  // n-th use of this accumulator buffer
+                if (use >= 1) {
+                  mbar_wait(&sm.d_empty[ch.e & 1], (use - 1) & 1u);
+                  tc_fence_after();
+                }
+              }
+              ch.tiles_in_chain += 1;
+            }
+            int nv = meta.nvalid - HALF * h;
+            nv = nv < 0 ? 0 : (nv > HALF ? HALF : nv);
+            const int nk = (nv + 7) >> 3;
+            const uint32_t d_addr = tbase + D_COL + NB * (ch.e & 1);
+            const uint64_t bdesc0 = make_smem_desc_kmajor_noswizzle(smem_u32(sm.B[h]), 128, B_SBO);
+            for (int ks = 0; ks < nk; ++ks) {
+              umma_tf32_ts(d_addr, tbase + A_COL + HALF * h + 8 * ks, bdesc0 + (uint64_t)((ks * 256) >> 4), idesc,
+                           !first);
+              first = false;
+            }
+            umma_commit(&sm.a_empty[h]);
+          }
+        }
+        umma_commit(&sm.d_full[ch.e & 1]);
+      }
+    } else {
+      // ======================================================================= operand warps 0..2
+      const uint32_t lane_taddr = tbase + ((uint32_t)(warp * 32) << 16);
+      float racc[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) racc[j] = 0.0f;
+      ChainState ch;
+      int chain_valid = 0;        // valid pixels accumulated into the current chain
+      int cur_slot = -1;
+      unsigned int inliers = 0;   // of the current item (warp 0 only reports)
+      // deferred drain of a finished chain
+      bool pend = false;
+      int pend_e = 0, pend_valid = 0, pend_slot = 0;
+      bool pend_item_end = false;
+      unsigned int pend_inliers = 0;
+
+      auto write_partial = [&](int slot, unsigned int inl) {
+        float* P = partials + (size_t)slot * kTcPartialFloats;
+        const int row = warp * 32 + lane;
+        if (row < kTcRows) {
+          float4* dst = reinterpret_cast<float4*>(P + row * kTcCols);
+#pragma unroll
+          for (int j = 0; j < kTcCols / 4; ++j)
+            dst[j] = make_float4(racc[4 * j], racc[4 * j + 1], racc[4 * j + 2], racc[4 * j + 3]);
+        }
+        if (warp == 0 && lane == 0) reinterpret_cast<unsigned int*>(P)[kTcRows * kTcCols] = inl;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) racc[j] = 0.0f;
+      };
+      auto drain = [&](int e, int valid) {
+        const int b = e & 1, use = e >> 1;
+        mbar_wait(&sm.d_full[b], use & 1u);
+        tc_fence_after();
+        if (valid > 0) {
+          uint32_t v[NB];
+          tmem_ld_x16(lane_taddr + D_COL + NB * b, v);
+          tmem_ld_x16(lane_taddr + D_COL + NB * b + 16, v + 16);
+          tmem_ld_x16(lane_taddr + D_COL + NB * b + 32, v + 32);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < NB; ++j) racc[j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.d_empty[b]);
+      };
+
+      for (int i = 0; i < ntiles; ++i) {
+        const int st = i % STAGES;
+        const int fb = i & 1;
+        mbar_wait(&sm.feat_full[fb], (i >> 1) & 1u);
+        const TileMeta meta = sm.meta[fb];
+        if (ch.starts_chain(i, meta)) {
+          if (i > 0) {
+            pend = true;
+            pend_e = ch.e;
+            pend_valid = chain_valid;
+            pend_item_end = meta.item_changed != 0;
+            pend_slot = cur_slot;
+            pend_inliers = inliers;
+          }
+          ch.e += 1;
+          ch.tiles_in_chain = 0;
+          chain_valid = 0;
+          if (meta.item_changed) {
+            cur_slot = meta.slot;
+            inliers = 0;
+          }
+        }
+        ch.tiles_in_chain += 1;
+        chain_valid += meta.nvalid;
+        inliers += (unsigned)meta.nvalid;
+
+        const uint32_t jc_base = smem_u32(sm.jc[st]) + 4u * lane;
+        const uint32_t sid_base = smem_u32(sm.sid[fb]);
+        const uint32_t feat_base = smem_u32(sm.feat[fb]);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          int nv = meta.nvalid - HALF * h;
+          nv = nv < 0 ? 0 : (nv > HALF ? HALF : nv);
+          const int nk = (nv + 7) >> 3;
+          // A/B half h was last read by the MMAs of tile i-1
+          mbar_wait(&sm.a_empty[h], (i & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t b_half = smem_u32(sm.B[h]);
+          for (int ks = 0; ks < nk; ++ks) {
+            const int c0 = HALF * h + 8 * ks;
+            uint32_t v[8];
+            if (warp < 2) {
+              const int4 ia = lds_i4(sid_base + 4u * c0), ib = lds_i4(sid_base + 4u * (c0 + 4));
+              const float4 sa = lds_f4(feat_base + 4u * c0), sb = lds_f4(feat_base + 4u * (c0 + 4));
+              const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+              const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+              float val[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) val[j] = sc[j] * lds_f32(jc_base + 128u * (uint32_t)ids[j]);
+              if (warp == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(val[j]);
+                const uint32_t baddr = b_half + (uint32_t)(lane >> 3) * B_SBO + (uint32_t)(2 * ks) * 128u +
+                                       (uint32_t)(lane & 7) * 16u;
+                sts_f4(baddr, val[0], val[1], val[2], val[3]);
+                sts_f4(baddr + 128u, val[4], val[5], val[6], val[7]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(val[j] - tf32_trunc(val[j]));
+              }
+            } else {
+              // pose / residual features: lanes 0-6 = h of feature 1+lane, lanes 7-13 = l of feature 1+(lane-7)
+              float val[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) val[j] = 0.0f;
+              if (lane < 14) {
+                const int f = 1 + (lane < 7 ? lane : lane - 7);
+                const float4 xa = lds_f4(feat_base + 4u * (f * TILE + c0)), xb = lds_f4(feat_base + 4u * (f * TILE + c0 + 4));
+                val[0] = xa.x; val[1] = xa.y; val[2] = xa.z; val[3] = xa.w;
+                val[4] = xb.x; val[5] = xb.y; val[6] = xb.z; val[7] = xb.w;
+                if (lane < 7) {
+                  const uint32_t row = 32u + (uint32_t)lane;
+                  const uint32_t baddr = b_half + (row >> 3) * B_SBO + (uint32_t)(2 * ks) * 128u + (row & 7u) * 16u;
+                  sts_f4(baddr, val[0], val[1], val[2], val[3]);
+                  sts_f4(baddr + 128u, val[4], val[5], val[6], val[7]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) val[j] = val[j] - tf32_trunc(val[j]);
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(val[j]);
+            }
+            tmem_st_x8(lane_taddr + A_COL + HALF * h + 8 * ks, v);
+          }
+          tmem_wait_st();
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.a_full[h]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.feat_empty[fb]);
+
+        if (pend) {  // the chain that ended before this tile: its MMAs completed long ago
+          drain(pend_e, pend_valid);
+          if (pend_item_end) write_partial(pend_slot, pend_inliers);
+          pend = false;
+        }
+      }
+      drain(ch.e, chain_valid);
+      write_partial(cur_slot, inliers);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc(tbase, TMEM_COLS);
+}
+
+}  // namespace
+
+// normalised ray tables of an item: xn[x] = (x - u0)/fx for x < W, then yn[y] = (y - v0)/fy for y < H
+__global__ void sfm_ray_tables_kernel(const SfmItemDev* __restrict__ items, float* __restrict__ tabs)
+{
+  (void)tabs;  // every item carries the address of its own table inside the scratch buffer
+  const SfmItemDev& I = items[blockIdx.x];
+  float* dst = const_cast<float*>(I.ray_tab);
+  for (uint32_t x = threadIdx.x; x < I.width; x += blockDim.x) dst[x] = ray_coord((float)x, I.u0, I.fx);
+  for (uint32_t y = threadIdx.x; y < I.height; y += blockDim.x) dst[I.width + y] = ray_coord((float)y, I.v0, I.fy);
+}
+
+bool sfm_tc_supported(int code_size) { return code_size == 32; }
+
+size_t sfm_tc_smem_bytes() { return sizeof(Smem); }
+
+cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, float* ray_tabs_dev,
+                          float* partials_dev, cudaStream_t stream, cudaEvent_t ev_start, cudaEvent_t ev_stop)
+{
+  const size_t smem = sizeof(Smem);
+  cudaError_t err = cudaFuncSetAttribute(sfm_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  sfm_ray_tables_kernel<<<plan.num_items, 256, 0, stream>>>(items_dev, ray_tabs_dev);
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  if (ev_start) cudaEventRecord(ev_start, stream);
+  sfm_step_tc_kernel<<<plan.num_ctas, THREADS, smem, stream>>>(items_dev, plan.num_items, plan.num_tiles, partials_dev);
+  if (ev_stop) cudaEventRecord(ev_stop, stream);
+  return cudaGetLastError();
+}
+
+}  // namespace dfk

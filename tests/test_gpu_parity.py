@@ -86,9 +86,11 @@ def test_sfm_run_step_matches_oracle(torch_mod, oracle, w, h, cs, extra):
     pair = synth.make_pair(w, h, cs, 1, seed=w + cs, code_sigma=0.5)
     L = pair.levels[0]
     dev = upload_level(torch, L, extra)
-    for delta in (0.1, 0.5):  # production / reference-test Huber thresholds (dense_sfm.h:38, ut_sfmaligner.cpp:69)
+    modes = ("fp32", "tf32x3") if cs == 32 else ("fp32",)
+    # production / reference-test Huber thresholds (dense_sfm.h:38, ut_sfmaligner.cpp:69) x Gram engines
+    for delta, mode in [(d, m) for d in (0.1, 0.5) for m in modes]:
         dev["valid0"].zero_()
-        al = SfmAligner(cs, SfmAlignerParams(sfmparams=DenseSfmParams(huber_delta=delta)), gram_mode="fp32")
+        al = SfmAligner(cs, SfmAlignerParams(sfmparams=DenseSfmParams(huber_delta=delta)), gram_mode=mode)
         g = al.RunStep(pair.pose0, pair.pose1, pair.code, L.cam, dev["img0"], dev["img1"], dev["dpt0"], dev["std0"],
                        dev["valid0"], dev["prx0_jac"], dev["grad1"])
         prm = oracle.default_params(huber_delta=delta)
@@ -97,7 +99,7 @@ def test_sfm_run_step_matches_oracle(torch_mod, oracle, w, h, cs, extra):
                                   precision="f32")
         o64 = oracle.sfm_run_step(pair.pose0, pair.pose1, L.cam, L.img0, L.img1, L.dpt0, None, L.prx_jac, L.grad1, prm,
                                   precision="f64")
-        compare_step(g, o32, o64, f"{w}x{h} C={cs} pitch+{extra} delta={delta}")
+        compare_step(g, o32, o64, f"{w}x{h} C={cs} pitch+{extra} delta={delta} gram={mode}")
         # valid0 side effect: exactly the oracle's mask
         v_gpu = dev["valid0"].cpu().numpy()
         assert np.array_equal(v_gpu, v_cpu)
@@ -110,14 +112,15 @@ def test_sfm_identity_pose_all_pixels_inliers(torch_mod, oracle):
     pair = synth.make_pair(320, 240, 32, 1, seed=5, identity_pose=True)
     L = pair.levels[0]
     dev = upload_level(torch, L)
-    al = SfmAligner(32, gram_mode="fp32")
-    g = al.RunStep(pair.pose0, pair.pose1, pair.code, L.cam, dev["img0"], dev["img1"], dev["dpt0"], None, dev["valid0"],
-                   dev["prx0_jac"], dev["grad1"])
     o32 = oracle.sfm_run_step(pair.pose0, pair.pose1, L.cam, L.img0, L.img1, L.dpt0, None, L.prx_jac, L.grad1)
     o64 = oracle.sfm_run_step(pair.pose0, pair.pose1, L.cam, L.img0, L.img1, L.dpt0, None, L.prx_jac, L.grad1,
                               precision="f64")
-    assert abs(g.inliers - (320 - 4) * (240 - 4)) <= 2 * (320 + 240)  # up to rounding on the border rows/cols
-    compare_step(g, o32, o64, "identity")
+    for mode in ("fp32", "tf32x3"):
+        al = SfmAligner(32, gram_mode=mode)
+        g = al.RunStep(pair.pose0, pair.pose1, pair.code, L.cam, dev["img0"], dev["img1"], dev["dpt0"], None,
+                       dev["valid0"], dev["prx0_jac"], dev["grad1"])
+        assert abs(g.inliers - (320 - 4) * (240 - 4)) <= 2 * (320 + 240)  # up to rounding on the border rows/cols
+        compare_step(g, o32, o64, f"identity gram={mode}")
 
 
 def test_sfm_no_overlap_gives_zero_system(torch_mod):
@@ -136,11 +139,12 @@ def test_sfm_no_overlap_gives_zero_system(torch_mod):
     assert float(dev["valid0"].abs().sum()) == 0.0
 
 
-def test_sfm_batch_matches_single_calls_and_is_deterministic(torch_mod):
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_sfm_batch_matches_single_calls_and_is_deterministic(torch_mod, mode):
     """a 4-level pyramid of 2 pairs in ONE launch == the per-level calls, bit for bit across runs"""
     torch = torch_mod
     from deepfactors_b200.aligners import SfmAligner
-    al = SfmAligner(32, gram_mode="fp32")
+    al = SfmAligner(32, gram_mode=mode)
     items, singles = [], []
     for s in range(2):
         pair = synth.make_pair(320, 240, 32, 4, seed=20 + s, code_sigma=0.3, phase=0.2 * s)
@@ -264,12 +268,12 @@ def test_error_reporting_is_loud(torch_mod):
     pair = synth.make_pair(160, 120, 32, 1)
     L = pair.levels[0]
     dev = upload_level(torch, L)
-    with pytest.raises(_lib.DfkError):  # mismatched view sizes
+    with pytest.raises((_lib.DfkError, ValueError)):  # mismatched view sizes
         al.RunStep(pair.pose0, pair.pose1, pair.code, L.cam, dev["img0"][:100], dev["img1"], dev["dpt0"], None,
                    dev["valid0"], dev["prx0_jac"], dev["grad1"])
     with pytest.raises(_lib.DfkError):  # threads must be a multiple of 32 (cu_sfmaligner.cpp:190)
         al.SetStepThreadsBlocks(33, 11)
     bad = SfmAligner(5)  # no kernel for this code size
-    with pytest.raises(_lib.DfkError):
+    with pytest.raises((_lib.DfkError, ValueError)):
         bad.RunStep(pair.pose0, pair.pose1, None, L.cam, dev["img0"], dev["img1"], dev["dpt0"], None, dev["valid0"],
                     dev["prx0_jac"], dev["grad1"])

@@ -44,9 +44,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
   return ok != 0;
 }
 
+// A waiting warp must not monopolise its sub-core's issue port (the arbiter favours some warp ids):
+// back off with nanosleep between polls.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
-  while (!mbar_try_wait(bar, parity)) {
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
+
+// Same, for long waits by a lone thread (MMA issuer): the suspend-time hint lets the hardware park the
+// thread until the phase completes instead of burning issue slots in a spin loop.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
+{
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (!ok) __nanosleep(128);
   }
 }
 

@@ -31,6 +31,8 @@
 // fp32 kernel.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "dfk_async.cuh"
 #include "dfk_geom.cuh"
@@ -45,8 +47,10 @@ constexpr int C = 32;
 constexpr int TILE = kTcTilePixels;  // 128
 constexpr int HALF = 64;
 constexpr int STAGES = 4;
-constexpr int FE_THREADS = 128;
-constexpr int THREADS = 256;
+constexpr int FE_GROUPS = 2;         // front-end group g handles the CTA's tiles i with i % 2 == g
+constexpr int FE_THREADS = 128;      // per group: one thread per pixel of a tile
+constexpr int OP_THREADS = 256;       // warps 0-2: operand group A (half 0), 3: control, 4-6: operand group B (half 1), 7: idle
+constexpr int THREADS = OP_THREADS + FE_GROUPS * FE_THREADS;
 constexpr int NB = 48;           // MMA N (39 used)
 constexpr int MM = 128;          // MMA M (78 used)
 constexpr int kFlushTiles = 8;   // TMEM accumulation chain length (tiles)
@@ -95,8 +99,8 @@ struct Smem {
   uint64_t d_full[2];
   uint64_t d_empty[2];
   TileMeta meta[2];
-  ItemSmem item;
-  int cnt[2][4];  // per feat buffer: a fast warp may start tile i+1 while a slow one still reads tile i's counts
+  ItemSmem item[FE_GROUPS];
+  int cnt[FE_GROUPS][2][4];  // [group][tile parity within the group]: a fast warp may run one tile ahead of a slow one
   uint32_t tmem_base;
 };
 
@@ -182,6 +186,15 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c,
 }
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
+// ---- optional phase timers (clock64 sums per role), enabled with the env var DFK_TC_DEBUG=1 ----------
+__device__ unsigned long long g_dbg[16];
+struct Tmr {
+  long long t;
+  bool on;
+  __device__ __forceinline__ void start() { if (on) t = clock64(); }
+  __device__ __forceinline__ void lap(unsigned long long& acc) { if (on) { const long long n = clock64(); acc += (unsigned long long)(n - t); t = n; } }
+};
+
 // chain bookkeeping shared (by construction) between the control thread and the operand warps
 struct ChainState {
   int e = -1;              // current chain index
@@ -193,7 +206,8 @@ struct ChainState {
 };
 
 __global__ void __launch_bounds__(THREADS, 2)
-sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_tiles, float* __restrict__ partials)
+sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_tiles, float* __restrict__ partials,
+                   int dbg)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -211,7 +225,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
     for (int s = 0; s < STAGES; ++s) mbar_init(&sm.tma_full[s], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm.feat_full[b], FE_THREADS);
-      mbar_init(&sm.feat_empty[b], 3);
+      mbar_init(&sm.feat_empty[b], 7);  // 2 x 3 operand warps + the control thread (it reads meta[b])
       mbar_init(&sm.a_full[b], 3);
       mbar_init(&sm.a_empty[b], 1);
       mbar_init(&sm.d_full[b], 1);
@@ -233,50 +247,61 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
   tc_fence_after();
   const uint32_t tbase = sm.tmem_base;
 
+  // register budget per role (warpgroup granularity): operand / control warps are lean, the front-end is not
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  }
+
   if (ntiles > 0) {
-    if (warp >= 4) {
-      // ======================================================================= front-end warps
-      const int ft = tid - 128;  // 0..127 = pixel slot
-      const int fwarp = warp - 4;
+    if (warp >= 8) {
+      // ======================================================================= front-end groups
+      const int grp = (warp - 8) >> 2;          // 0 / 1
+      const int ft = (tid - OP_THREADS) & (FE_THREADS - 1);  // 0..127 = pixel slot
+      const int fwarp = (warp - 8) & 3;
+      const uint32_t bar_id = 1 + grp;
+      ItemSmem& I = sm.item[grp];
       int it = 0;
-      while (it + 1 < num_items && (uint32_t)g_lo >= items[it].tile_begin + items[it].num_tiles) ++it;
-      int it_pf = it;
+      int it_pf = 0;
       uint32_t tma_phase_bits = 0;
       int cur_item = -1;
-      if (ft == 0) {
-        for (int j = 0; j < 2 && j < ntiles; ++j) {  // prefetch distance 2
-          const int g = g_lo + j;
-          while ((uint32_t)g >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
-          if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, g, j % STAGES);
-        }
+      Tmr tm{0, dbg != 0 && ft == 0};
+      unsigned long long t_tma = 0, t_geo = 0, t_fe_wait = 0, t_fe_write = 0, t_issue_fe = 0;
+      if (ft == 0 && grp < ntiles) {  // prologue: this group's first tile
+        const int g = g_lo + grp;
+        while ((uint32_t)g >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
+        if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, g, grp % STAGES);
       }
-      for (int i = 0; i < ntiles; ++i) {
+      for (int i = grp; i < ntiles; i += FE_GROUPS) {
         const int g = g_lo + i;
         const int st = i % STAGES;
-        const int fb = i & 1;
+        const int fb = grp;  // == i & 1
         while ((uint32_t)g >= items[it].tile_begin + items[it].num_tiles) ++it;
-        const bool changed = (it != cur_item);
-        if (changed) {
-          named_bar_sync(1, FE_THREADS);
-          load_item(sm.item, items[it], ft, cta);
+        // the tile sequence enters a new item here (relative to tile i-1, which the other group handles)
+        const bool seq_changed = (i == 0) || ((uint32_t)(g - 1) < items[it].tile_begin);
+        if (it != cur_item) {
+          named_bar_sync(bar_id, FE_THREADS);
+          load_item(I, items[it], ft, cta);
           cur_item = it;
-          named_bar_sync(1, FE_THREADS);
+          named_bar_sync(bar_id, FE_THREADS);
         }
-        const ItemSmem& I = sm.item;
         const uint32_t k = (uint32_t)g - I.tile_begin;
         const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
         const uint32_t p0 = tau * TILE;
         const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
         const bool bulk = (I.flags & ITEM_FLAG_BULK) != 0;
+        tm.start();
         if (bulk) {
-          mbar_wait(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
+          mbar_wait_parked(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
           tma_phase_bits ^= (1u << st);
         } else {
-          // the stage was last read by the operand warps of tile i-4: released before feat_empty(i-2) was
+          // stage st was last read by the operand warps of tile i-4, released before feat_empty(i-2) completed
           coop_tile_loads(sm, I, p0, n, st, ft);
-          named_bar_sync(1, FE_THREADS);
+          named_bar_sync(bar_id, FE_THREADS);
         }
 
+        tm.lap(t_tma);
         float feat[8];
         bool ok = false;
         const uint32_t s = ft;
@@ -308,22 +333,18 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         }
         const unsigned bal = __ballot_sync(0xffffffffu, ok);
         const int rank = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) sm.cnt[fb][fwarp] = __popc(bal);
+        const int cpar = (i >> 1) & 1;
+        if (lane == 0) sm.cnt[grp][cpar][fwarp] = __popc(bal);
+        tm.lap(t_geo);
         // feat[fb] / sid[fb] of tile i-2 must have been consumed; this also frees ring stage (i+2)%4
-        mbar_wait(&sm.feat_empty[fb], ((i >> 1) & 1u) ^ 1u);
-        named_bar_sync(1, FE_THREADS);
-        if (ft == 0) {
-          const int gn = g + 2;
-          if (gn < g_hi) {
-            while ((uint32_t)gn >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
-            if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, gn, (i + 2) % STAGES);
-          }
-        }
+        mbar_wait_parked(&sm.feat_empty[fb], ((i >> 1) & 1u) ^ 1u);
+        named_bar_sync(bar_id, FE_THREADS);
+        tm.lap(t_fe_wait);
         int nvalid = 0, base = 0;
 #pragma unroll
         for (int w2 = 0; w2 < 4; ++w2) {
           if (w2 == fwarp) base = nvalid;
-          nvalid += sm.cnt[fb][w2];
+          nvalid += sm.cnt[grp][cpar][w2];
         }
         if (ok) {
           const int c = base + rank;
@@ -342,10 +363,23 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         }
         if (ft == 0) {
           sm.meta[fb].nvalid = nvalid;
-          sm.meta[fb].item_changed = changed ? 1 : 0;
+          sm.meta[fb].item_changed = seq_changed ? 1 : 0;
           sm.meta[fb].slot = (int)I.slot;
         }
         mbar_arrive(&sm.feat_full[fb]);
+        tm.lap(t_fe_write);
+        if (ft == 0) {  // prefetch this group's next tile (stage freed by the feat_empty wait above)
+          const int gn = g + FE_GROUPS;
+          if (gn < g_hi) {
+            while ((uint32_t)gn >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
+            if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, gn, (i + FE_GROUPS) % STAGES);
+          }
+        }
+        tm.lap(t_issue_fe);
+      }
+      if (tm.on) {
+        atomicAdd(&g_dbg[0], t_tma); atomicAdd(&g_dbg[1], t_geo); atomicAdd(&g_dbg[2], t_fe_wait);
+        atomicAdd(&g_dbg[3], t_fe_write); atomicAdd(&g_dbg[13], t_issue_fe);
       }
     } else if (warp == 3) {
       // ======================================================================= control warp
@@ -353,14 +387,19 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         const uint32_t idesc = make_idesc_tf32(MM, NB);
         ChainState ch;
         bool first = true;
+        Tmr tm{0, dbg != 0};
+        unsigned long long t_afull = 0, t_issue = 0;
         for (int i = 0; i < ntiles; ++i) {
           const int fb = i & 1;
           TileMeta meta{};
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(&sm.a_full[h], i & 1u);
+            tm.start();
+            mbar_wait_parked(&sm.a_full[h], i & 1u);
             tc_fence_after();
+            tm.lap(t_afull);
             if (h == 0) {
               meta = sm.meta[fb];
+              mbar_arrive(&sm.feat_empty[fb]);  // meta[fb] may now be overwritten (once the operand warps agree)
               if (ch.starts_chain(i, meta)) {
                 if (i > 0) umma_commit(&sm.d_full[ch.e & 1]);
                 ch.e += 1;
@@ -368,7 +407,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
                 first = true;
                 const int use = ch.e >> 1;  // n-th use of this accumulator buffer
                 if (use >= 1) {
-                  mbar_wait(&sm.d_empty[ch.e & 1], (use - 1) & 1u);
+                  mbar_wait_parked(&sm.d_empty[ch.e & 1], (use - 1) & 1u);
                   tc_fence_after();
                 }
               }
@@ -385,76 +424,104 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
               first = false;
             }
             umma_commit(&sm.a_empty[h]);
+            tm.lap(t_issue);
           }
         }
         umma_commit(&sm.d_full[ch.e & 1]);
+        if (tm.on) { atomicAdd(&g_dbg[4], t_afull); atomicAdd(&g_dbg[5], t_issue); }
       }
-    } else {
-      // ======================================================================= operand warps 0..2
-      const uint32_t lane_taddr = tbase + ((uint32_t)(warp * 32) << 16);
-      float racc[NB];
-#pragma unroll
-      for (int j = 0; j < NB; ++j) racc[j] = 0.0f;
+    } else if ((warp & 3) != 3) {
+      // ======================================================================= operand warps
+      // group A (warps 0-2) builds half 0 of every tile and drains the accumulators; group B (warps 4-6)
+      // builds half 1.  ow: 0 = code-h (+B), 1 = code-l, 2 = pose/residual h+l.
+      const int ogrp = warp >> 2;
+      const int ow = warp & 3;
+      const uint32_t lane_taddr = tbase + ((uint32_t)(ow * 32) << 16);
+      const int row = ow * 32 + lane;  // TMEM lane == row of the partial
       ChainState ch;
       int chain_valid = 0;        // valid pixels accumulated into the current chain
       int cur_slot = -1;
-      unsigned int inliers = 0;   // of the current item (warp 0 only reports)
+      bool slot_fresh = true;     // the current item's partial has not been written yet by this CTA
+      unsigned int inliers = 0;   // of the current item (warp 0 reports)
       // deferred drain of a finished chain
       bool pend = false;
       int pend_e = 0, pend_valid = 0, pend_slot = 0;
-      bool pend_item_end = false;
+      bool pend_fresh = false, pend_item_end = false;
       unsigned int pend_inliers = 0;
 
-      auto write_partial = [&](int slot, unsigned int inl) {
-        float* P = partials + (size_t)slot * kTcPartialFloats;
-        const int row = warp * 32 + lane;
-        if (row < kTcRows) {
-          float4* dst = reinterpret_cast<float4*>(P + row * kTcCols);
-#pragma unroll
-          for (int j = 0; j < kTcCols / 4; ++j)
-            dst[j] = make_float4(racc[4 * j], racc[4 * j + 1], racc[4 * j + 2], racc[4 * j + 3]);
-        }
-        if (warp == 0 && lane == 0) reinterpret_cast<unsigned int*>(P)[kTcRows * kTcCols] = inl;
-#pragma unroll
-        for (int j = 0; j < NB; ++j) racc[j] = 0.0f;
-      };
-      auto drain = [&](int e, int valid) {
+      // Move a finished chain TMEM -> the CTA's partial in global memory (single writer, fixed order).
+      // fresh: first chain of the item in this CTA (store), else read-modify-write in round-to-nearest fp32.
+      auto drain = [&](int e, int valid, int slot, bool fresh, bool item_end, unsigned int inl) {
         const int b = e & 1, use = e >> 1;
+        float* P = partials + (size_t)slot * kTcPartialFloats;
+        float4* dst = reinterpret_cast<float4*>(P + row * kTcCols);
+        const bool have_row = row < kTcRows;
         mbar_wait(&sm.d_full[b], use & 1u);
         tc_fence_after();
-        if (valid > 0) {
-          uint32_t v[NB];
-          tmem_ld_x16(lane_taddr + D_COL + NB * b, v);
-          tmem_ld_x16(lane_taddr + D_COL + NB * b + 16, v + 16);
-          tmem_ld_x16(lane_taddr + D_COL + NB * b + 32, v + 32);
-          tmem_wait_ld();
+        // three passes of 16 accumulator columns keep the register footprint small
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const int nq = pass < 2 ? 4 : (kTcCols - 32) / 4;  // float4 per pass (columns 40..47 are padding)
+          float4 acc[4];
 #pragma unroll
-          for (int j = 0; j < NB; ++j) racc[j] += __uint_as_float(v[j]);
+          for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (have_row && !fresh) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nq) acc[j] = __ldcg(dst + 4 * pass + j);
+          }
+          if (valid > 0) {
+            uint32_t v[16];
+            tmem_ld_x16(lane_taddr + D_COL + NB * b + 16 * pass, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j].x += __uint_as_float(v[4 * j]);
+              acc[j].y += __uint_as_float(v[4 * j + 1]);
+              acc[j].z += __uint_as_float(v[4 * j + 2]);
+              acc[j].w += __uint_as_float(v[4 * j + 3]);
+            }
+          }
+          if (have_row && (valid > 0 || fresh)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nq) __stcg(dst + 4 * pass + j, acc[j]);
+          }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.d_empty[b]);
+        if (item_end && ow == 0 && lane == 0) reinterpret_cast<unsigned int*>(P)[kTcRows * kTcCols] = inl;
       };
 
+      Tmr tm{0, dbg != 0 && warp == 0 && lane == 0};
+      const bool is_a = (ogrp == 0);
+      unsigned long long t_ffull = 0, t_aempty = 0, t_build = 0, t_sync = 0, t_drain = 0, t_total = 0;
+      const long long t_begin = tm.on ? clock64() : 0;
       for (int i = 0; i < ntiles; ++i) {
         const int st = i % STAGES;
         const int fb = i & 1;
+        tm.start();
         mbar_wait(&sm.feat_full[fb], (i >> 1) & 1u);
+        tm.lap(t_ffull);
         const TileMeta meta = sm.meta[fb];
-        if (ch.starts_chain(i, meta)) {
+        if (is_a && ch.starts_chain(i, meta)) {
           if (i > 0) {
             pend = true;
             pend_e = ch.e;
             pend_valid = chain_valid;
             pend_item_end = meta.item_changed != 0;
             pend_slot = cur_slot;
+            pend_fresh = slot_fresh;
             pend_inliers = inliers;
+            slot_fresh = false;
           }
           ch.e += 1;
           ch.tiles_in_chain = 0;
           chain_valid = 0;
           if (meta.item_changed) {
             cur_slot = meta.slot;
+            slot_fresh = true;
             inliers = 0;
           }
         }
@@ -462,82 +529,101 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         chain_valid += meta.nvalid;
         inliers += (unsigned)meta.nvalid;
 
-        const uint32_t jc_base = smem_u32(sm.jc[st]) + 4u * lane;
-        const uint32_t sid_base = smem_u32(sm.sid[fb]);
-        const uint32_t feat_base = smem_u32(sm.feat[fb]);
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+        // plain (non-volatile) shared-memory accesses: the compiler is free to overlap the loads of
+        // several chunks; the mbarrier waits / fences around the loop carry the "memory" clobbers
+        const float* __restrict__ jcp = sm.jc[st] + lane;
+        const int4* __restrict__ sidp = reinterpret_cast<const int4*>(sm.sid[fb]);
+        const float4* __restrict__ featp = reinterpret_cast<const float4*>(sm.feat[fb]);
+        {
+          const int h = ogrp;
           int nv = meta.nvalid - HALF * h;
           nv = nv < 0 ? 0 : (nv > HALF ? HALF : nv);
           const int nk = (nv + 7) >> 3;
           // A/B half h was last read by the MMAs of tile i-1
+          tm.start();
           mbar_wait(&sm.a_empty[h], (i & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t b_half = smem_u32(sm.B[h]);
-          for (int ks = 0; ks < nk; ++ks) {
-            const int c0 = HALF * h + 8 * ks;
-            uint32_t v[8];
-            if (warp < 2) {
-              const int4 ia = lds_i4(sid_base + 4u * c0), ib = lds_i4(sid_base + 4u * (c0 + 4));
-              const float4 sa = lds_f4(feat_base + 4u * c0), sb = lds_f4(feat_base + 4u * (c0 + 4));
-              const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
-              const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+          tm.lap(t_aempty);
+          unsigned char* bh = sm.B[h];
+          const uint32_t a_taddr = lane_taddr + A_COL + HALF * h;
+          if (ow < 2) {
+            float4* brow = reinterpret_cast<float4*>(bh + (uint32_t)(lane >> 3) * B_SBO + (uint32_t)(lane & 7) * 16u);
+#pragma unroll 2
+            for (int ks = 0; ks < nk; ++ks) {
+              const int c4 = (HALF * h + 8 * ks) >> 2;
+              const int4 ia = sidp[c4], ib = sidp[c4 + 1];
+              const float4 sa = featp[c4], sb = featp[c4 + 1];
               float val[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) val[j] = sc[j] * lds_f32(jc_base + 128u * (uint32_t)ids[j]);
-              if (warp == 0) {
+              val[0] = sa.x * jcp[ia.x * C]; val[1] = sa.y * jcp[ia.y * C];
+              val[2] = sa.z * jcp[ia.z * C]; val[3] = sa.w * jcp[ia.w * C];
+              val[4] = sb.x * jcp[ib.x * C]; val[5] = sb.y * jcp[ib.y * C];
+              val[6] = sb.z * jcp[ib.z * C]; val[7] = sb.w * jcp[ib.w * C];
+              uint32_t v[8];
+              if (ow == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(val[j]);
-                const uint32_t baddr = b_half + (uint32_t)(lane >> 3) * B_SBO + (uint32_t)(2 * ks) * 128u +
-                                       (uint32_t)(lane & 7) * 16u;
-                sts_f4(baddr, val[0], val[1], val[2], val[3]);
-                sts_f4(baddr + 128u, val[4], val[5], val[6], val[7]);
+                brow[16 * ks] = make_float4(val[0], val[1], val[2], val[3]);      // k-chunk 2ks   (128 B apart)
+                brow[16 * ks + 8] = make_float4(val[4], val[5], val[6], val[7]);  // k-chunk 2ks+1
               } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(val[j] - tf32_trunc(val[j]));
               }
-            } else {
-              // pose / residual features: lanes 0-6 = h of feature 1+lane, lanes 7-13 = l of feature 1+(lane-7)
+              tmem_st_x8(a_taddr + 8 * ks, v);
+            }
+          } else {
+            // pose / residual features: lanes 0-6 = h of feature 1+lane, lanes 7-13 = l of feature 1+(lane-7)
+            const int f = 1 + (lane < 7 ? lane : (lane < 14 ? lane - 7 : 0));
+            const float4* fp = featp + f * (TILE / 4);
+            const uint32_t brow_i = 32u + (uint32_t)(lane < 7 ? lane : 0);
+            float4* brow = reinterpret_cast<float4*>(bh + (brow_i >> 3) * B_SBO + (brow_i & 7u) * 16u);
+#pragma unroll 2
+            for (int ks = 0; ks < nk; ++ks) {
+              const int c4 = (HALF * h + 8 * ks) >> 2;
               float val[8];
+              const float4 xa = fp[c4], xb = fp[c4 + 1];
+              val[0] = xa.x; val[1] = xa.y; val[2] = xa.z; val[3] = xa.w;
+              val[4] = xb.x; val[5] = xb.y; val[6] = xb.z; val[7] = xb.w;
+              if (lane < 7) {
+                brow[16 * ks] = xa;
+                brow[16 * ks + 8] = xb;
+              } else if (lane < 14) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) val[j] = 0.0f;
-              if (lane < 14) {
-                const int f = 1 + (lane < 7 ? lane : lane - 7);
-                const float4 xa = lds_f4(feat_base + 4u * (f * TILE + c0)), xb = lds_f4(feat_base + 4u * (f * TILE + c0 + 4));
-                val[0] = xa.x; val[1] = xa.y; val[2] = xa.z; val[3] = xa.w;
-                val[4] = xb.x; val[5] = xb.y; val[6] = xb.z; val[7] = xb.w;
-                if (lane < 7) {
-                  const uint32_t row = 32u + (uint32_t)lane;
-                  const uint32_t baddr = b_half + (row >> 3) * B_SBO + (uint32_t)(2 * ks) * 128u + (row & 7u) * 16u;
-                  sts_f4(baddr, val[0], val[1], val[2], val[3]);
-                  sts_f4(baddr + 128u, val[4], val[5], val[6], val[7]);
-                } else {
+                for (int j = 0; j < 8; ++j) val[j] = val[j] - tf32_trunc(val[j]);
+              } else {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) val[j] = val[j] - tf32_trunc(val[j]);
-                }
+                for (int j = 0; j < 8; ++j) val[j] = 0.0f;
               }
+              uint32_t v[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(val[j]);
+              tmem_st_x8(a_taddr + 8 * ks, v);
             }
-            tmem_st_x8(lane_taddr + A_COL + HALF * h + 8 * ks, v);
           }
+          tm.lap(t_build);
           tmem_wait_st();
           fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.a_full[h]);
+          tm.lap(t_sync);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.feat_empty[fb]);
+        tm.start();
 
-        if (pend) {  // the chain that ended before this tile: its MMAs completed long ago
-          drain(pend_e, pend_valid);
-          if (pend_item_end) write_partial(pend_slot, pend_inliers);
+        if (is_a && pend) {  // the chain that ended before this tile: its MMAs completed long ago
+          drain(pend_e, pend_valid, pend_slot, pend_fresh, pend_item_end, pend_inliers);
           pend = false;
         }
+        tm.lap(t_drain);
       }
-      drain(ch.e, chain_valid);
-      write_partial(cur_slot, inliers);
+      if (is_a) drain(ch.e, chain_valid, cur_slot, slot_fresh, true, inliers);
+      if (tm.on) {
+        t_total = (unsigned long long)(clock64() - t_begin);
+        atomicAdd(&g_dbg[6], t_ffull); atomicAdd(&g_dbg[7], t_aempty); atomicAdd(&g_dbg[8], t_build);
+        atomicAdd(&g_dbg[9], t_sync); atomicAdd(&g_dbg[10], t_drain); atomicAdd(&g_dbg[11], t_total);
+        atomicAdd(&g_dbg[12], (unsigned long long)ntiles);
+      }
     }
   }
 
@@ -571,9 +657,27 @@ cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan
   sfm_ray_tables_kernel<<<plan.num_items, 256, 0, stream>>>(items_dev, ray_tabs_dev);
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
+  static const int dbg = []() { const char* e = getenv("DFK_TC_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
+  if (dbg) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbolAsync(g_dbg, z, sizeof(z), 0, cudaMemcpyHostToDevice, stream);
+  }
   if (ev_start) cudaEventRecord(ev_start, stream);
-  sfm_step_tc_kernel<<<plan.num_ctas, THREADS, smem, stream>>>(items_dev, plan.num_items, plan.num_tiles, partials_dev);
+  sfm_step_tc_kernel<<<plan.num_ctas, THREADS, smem, stream>>>(items_dev, plan.num_items, plan.num_tiles, partials_dev,
+                                                              dbg);
   if (ev_stop) cudaEventRecord(ev_stop, stream);
+  if (dbg) {
+    unsigned long long v[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(v, g_dbg, sizeof(v));
+    const double nt = v[12] ? (double)v[12] : 1.0;
+    fprintf(stderr,
+            "[dfk tc dbg] ctas=%d tiles=%d | per tile cycles: FE(g0+g1 thread0) tma_wait %.0f geom %.0f feat_empty_wait %.0f "
+            "write %.0f tma_issue %.0f | CTRL a_full_wait %.0f issue %.0f | OP feat_full_wait %.0f a_empty_wait %.0f build %.0f sync %.0f "
+            "drain %.0f total %.0f\n",
+            plan.num_ctas, plan.num_tiles, v[0] / nt, v[1] / nt, v[2] / nt, v[3] / nt, v[13] / nt, v[4] / nt, v[5] / nt, v[6] / nt,
+            v[7] / nt, v[8] / nt, v[9] / nt, v[10] / nt, v[11] / nt);
+  }
   return cudaGetLastError();
 }
 

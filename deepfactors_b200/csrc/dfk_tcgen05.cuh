@@ -41,9 +41,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // taddr = tmem_base + (lane_base << 16) + column, lane_base = 32 * (warp_id % 4).
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&v)[8])
 {
+  // no "memory" clobber: the instruction touches registers and TMEM only, so ordinary shared-memory
+  // loads of the next chunk may be scheduled across it (ordering vs. tcgen05.wait::st comes from volatile)
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
-               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]));
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

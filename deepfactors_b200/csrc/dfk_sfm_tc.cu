@@ -92,6 +92,7 @@ struct Smem {
   alignas(16) float feat[2][8][TILE];  // K-major per-pixel scalars of the compacted pixels: s, wa0..5, wr
   alignas(16) int sid[2][TILE];        // slot (row of the jc stage) of each compacted pixel
   alignas(8) uint64_t tma_full[STAGES];
+  uint64_t stage_empty[STAGES];  // the operand warps are done with the ring stage
   uint64_t feat_full[2];
   uint64_t feat_empty[2];
   uint64_t a_full[2];
@@ -133,6 +134,29 @@ __device__ __forceinline__ void issue_tile_loads(Smem& sm, const SfmItemDev* __r
   const SfmItemDev& I = items[it];
   const uint32_t k = (uint32_t)g - I.tile_begin;
   const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
+  const uint32_t p0 = tau * TILE;
+  const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
+  const uint32_t W = I.width;
+  uint32_t y = p0 / W;
+  uint32_t x = p0 - y * W;
+  mbar_arrive_expect_tx(&sm.tma_full[st], n * (C + 2) * 4u);
+  uint32_t slot = 0;
+  while (slot < n) {
+    const uint32_t seg = min(W - x, n - slot);
+    bulk_g2s(&sm.jc[st][slot * C], I.jac + (size_t)y * I.jac_pitch + (size_t)x * C, seg * C * 4u, &sm.tma_full[st]);
+    bulk_g2s(&sm.img0[st][slot], I.img0 + (size_t)y * I.img0_pitch + x, seg * 4u, &sm.tma_full[st]);
+    bulk_g2s(&sm.dpt0[st][slot], I.dpt0 + (size_t)y * I.dpt0_pitch + x, seg * 4u, &sm.tma_full[st]);
+    slot += seg;
+    x = 0;
+    ++y;
+  }
+}
+
+// Same, from the front-end group's shared-memory copy of the item (no global loads, 32-bit arithmetic).
+__device__ __forceinline__ void issue_tile_loads_smem(Smem& sm, const ItemSmem& I, int g, int st)
+{
+  const uint32_t k = (uint32_t)g - I.tile_begin;
+  const uint32_t tau = (k * I.perm_mul) % I.num_tiles;  // host guarantees k * perm_mul < 2^32
   const uint32_t p0 = tau * TILE;
   const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
   const uint32_t W = I.width;
@@ -222,11 +246,14 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(&sm.tma_full[s], 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sm.tma_full[s], 1);
+      mbar_init(&sm.stage_empty[s], 6);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm.feat_full[b], FE_THREADS);
       mbar_init(&sm.feat_empty[b], 7);  // 2 x 3 operand warps + the control thread (it reads meta[b])
-      mbar_init(&sm.a_full[b], 3);
+      mbar_init(&sm.a_full[b], 6);
       mbar_init(&sm.a_empty[b], 1);
       mbar_init(&sm.d_full[b], 1);
       mbar_init(&sm.d_empty[b], 3);
@@ -263,16 +290,10 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       const uint32_t bar_id = 1 + grp;
       ItemSmem& I = sm.item[grp];
       int it = 0;
-      int it_pf = 0;
       uint32_t tma_phase_bits = 0;
       int cur_item = -1;
       Tmr tm{0, dbg != 0 && ft == 0};
       unsigned long long t_tma = 0, t_geo = 0, t_fe_wait = 0, t_fe_write = 0, t_issue_fe = 0;
-      if (ft == 0 && grp < ntiles) {  // prologue: this group's first tile
-        const int g = g_lo + grp;
-        while ((uint32_t)g >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
-        if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, g, grp % STAGES);
-      }
       for (int i = grp; i < ntiles; i += FE_GROUPS) {
         const int g = g_lo + i;
         const int st = i % STAGES;
@@ -291,6 +312,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         const uint32_t p0 = tau * TILE;
         const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
         const bool bulk = (I.flags & ITEM_FLAG_BULK) != 0;
+        const uint32_t s = ft;
+        const uint32_t px_lin = p0 + (s < n ? s : 0u);
+        const uint32_t py = px_lin / I.width, pxx = px_lin - py * I.width;
+        const float xn = __ldg(I.ray_tab + pxx);              // in flight while the tile lands
+        const float yn = __ldg(I.ray_tab + I.width + py);
         tm.start();
         if (bulk) {
           mbar_wait_parked(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
@@ -304,13 +330,9 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         tm.lap(t_tma);
         float feat[8];
         bool ok = false;
-        const uint32_t s = ft;
         if (s < n) {
-          const uint32_t p = p0 + s;
-          const uint32_t y = p / I.width, x = p - y * I.width;
+          const uint32_t y = py, x = pxx;
           const float d = sm.dpt0[st][s];
-          const float xn = __ldg(I.ray_tab + x);
-          const float yn = __ldg(I.ray_tab + I.width + y);
           const Warped w = warp_ray(xn, yn, d, I.q, I.t, I.fx, I.fy, I.u0, I.v0, I.border, I.ulim, I.vlim, I.min_dpt);
           if (w.valid) {
             ok = true;
@@ -346,19 +368,39 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           if (w2 == fwarp) base = nvalid;
           nvalid += sm.cnt[grp][cpar][w2];
         }
+        // In-place compaction of the staged code-Jacobian rows, scaled by s = w*e on the way:
+        // row c of the stage becomes the c-th VALID pixel's  s * jc[0..31]  (what the operand warps feed to
+        // the tensor core).  Rotated float4 order keeps both the reads (row = slot) and the writes
+        // (row = compacted index) free of bank conflicts.  A pixel never moves up (c <= slot), but rows are
+        // read by other threads than they are written by, hence the barrier between the two phases.
+        float4 rowv[C / 4];
+        if (ok) {
+          const float4* src = reinterpret_cast<const float4*>(&sm.jc[st][s * C]);
+#pragma unroll
+          for (int k4 = 0; k4 < C / 4; ++k4) rowv[k4] = src[(k4 + lane) & (C / 4 - 1)];
+        }
+        named_bar_sync(bar_id, FE_THREADS);
         if (ok) {
           const int c = base + rank;
-          sm.sid[fb][c] = (int)s;
+          const float sc = feat[0];
+          float4* dst = reinterpret_cast<float4*>(&sm.jc[st][c * C]);
 #pragma unroll
-          for (int f = 0; f < 8; ++f) sm.feat[fb][f][c] = feat[f];
+          for (int k4 = 0; k4 < C / 4; ++k4) {
+            const float4 v = rowv[k4];
+            dst[(k4 + lane) & (C / 4 - 1)] = make_float4(sc * v.x, sc * v.y, sc * v.z, sc * v.w);
+          }
+#pragma unroll
+          for (int f = 1; f < 8; ++f) sm.feat[fb][f][c] = feat[f];
         }
         // pad the compacted list to a multiple of 8 with "pixels" that contribute exactly zero
         if (ft < 8) {
           const int c = nvalid + ft;
           if (c < ((nvalid + 7) & ~7)) {
-            sm.sid[fb][c] = TILE;  // the all-zero jc row
+            float4* dst = reinterpret_cast<float4*>(&sm.jc[st][c * C]);
 #pragma unroll
-            for (int f = 0; f < 8; ++f) sm.feat[fb][f][c] = 0.0f;
+            for (int k4 = 0; k4 < C / 4; ++k4) dst[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int f = 1; f < 8; ++f) sm.feat[fb][f][c] = 0.0f;
           }
         }
         if (ft == 0) {
@@ -368,13 +410,6 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         }
         mbar_arrive(&sm.feat_full[fb]);
         tm.lap(t_fe_write);
-        if (ft == 0) {  // prefetch this group's next tile (stage freed by the feat_empty wait above)
-          const int gn = g + FE_GROUPS;
-          if (gn < g_hi) {
-            while ((uint32_t)gn >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
-            if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, gn, (i + FE_GROUPS) % STAGES);
-          }
-        }
         tm.lap(t_issue_fe);
       }
       if (tm.on) {
@@ -430,6 +465,19 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         umma_commit(&sm.d_full[ch.e & 1]);
         if (tm.on) { atomicAdd(&g_dbg[4], t_afull); atomicAdd(&g_dbg[5], t_issue); }
       }
+    } else if (warp == 7) {
+      // ======================================================================= TMA producer (one thread)
+      // Tile j is issued as soon as its ring stage is free (tile j-4 consumed), i.e. up to three tiles ahead of
+      // the operand warps; issuing bulk copies costs hundreds of cycles apiece, so it lives on its own warp.
+      if (lane == 0) {
+        int it_pf = 0;
+        for (int j = 0; j < ntiles; ++j) {
+          const int g = g_lo + j;
+          if (j >= STAGES) mbar_wait_parked(&sm.stage_empty[j % STAGES], ((j / STAGES) - 1) & 1u);
+          while ((uint32_t)g >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
+          if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, g, j % STAGES);
+        }
+      }
     } else if ((warp & 3) != 3) {
       // ======================================================================= operand warps
       // group A (warps 0-2) builds half 0 of every tile and drains the accumulators; group B (warps 4-6)
@@ -454,38 +502,38 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       auto drain = [&](int e, int valid, int slot, bool fresh, bool item_end, unsigned int inl) {
         const int b = e & 1, use = e >> 1;
         float* P = partials + (size_t)slot * kTcPartialFloats;
-        float4* dst = reinterpret_cast<float4*>(P + row * kTcCols);
         const bool have_row = row < kTcRows;
         mbar_wait(&sm.d_full[b], use & 1u);
         tc_fence_after();
-        // three passes of 16 accumulator columns keep the register footprint small
+        // three passes of 16 accumulator columns keep the register footprint small.  The first chain of an
+        // item in this CTA stores, later chains add with fire-and-forget red.global.add.f32: this thread is the
+        // only writer of its row and issues its updates in program order, so the sum order is fixed.
+        if (valid > 0 || fresh) {
 #pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const int nq = pass < 2 ? 4 : (kTcCols - 32) / 4;  // float4 per pass (columns 40..47 are padding)
-          float4 acc[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (have_row && !fresh) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < nq) acc[j] = __ldcg(dst + 4 * pass + j);
-          }
-          if (valid > 0) {
+          for (int pass = 0; pass < 3; ++pass) {
+            const int nq = pass < 2 ? 4 : (kTcCols - 32) / 4;  // float4 per pass (columns 40..47 are padding)
             uint32_t v[16];
-            tmem_ld_x16(lane_taddr + D_COL + NB * b + 16 * pass, v);
-            tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[j].x += __uint_as_float(v[4 * j]);
-              acc[j].y += __uint_as_float(v[4 * j + 1]);
-              acc[j].z += __uint_as_float(v[4 * j + 2]);
-              acc[j].w += __uint_as_float(v[4 * j + 3]);
+            for (int j = 0; j < 16; ++j) v[j] = 0u;
+            if (valid > 0) {
+              tmem_ld_x16(lane_taddr + D_COL + NB * b + 16 * pass, v);
+              tmem_wait_ld();
             }
-          }
-          if (have_row && (valid > 0 || fresh)) {
+            if (have_row) {
+              float* drow = P + row * kTcCols + 16 * pass;
+              if (fresh) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < nq) __stcg(dst + 4 * pass + j, acc[j]);
+                for (int j = 0; j < 4; ++j)
+                  if (j < nq)
+                    __stcg(reinterpret_cast<float4*>(drow) + j,
+                           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (j < 4 * nq) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(drow + j), "f"(__uint_as_float(v[j])) : "memory");
+              }
+            }
           }
         }
         tc_fence_before();
@@ -530,12 +578,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         inliers += (unsigned)meta.nvalid;
 
         // plain (non-volatile) shared-memory accesses: the compiler is free to overlap the loads of
-        // several chunks; the mbarrier waits / fences around the loop carry the "memory" clobbers
-        const float* __restrict__ jcp = sm.jc[st] + lane;
-        const int4* __restrict__ sidp = reinterpret_cast<const int4*>(sm.sid[fb]);
+        // several chunks; the mbarrier waits / fences around the loops carry the "memory" clobbers
+        const float* __restrict__ vrow = sm.jc[st] + lane;  // compacted, pre-scaled rows: vrow[c * C]
         const float4* __restrict__ featp = reinterpret_cast<const float4*>(sm.feat[fb]);
-        {
-          const int h = ogrp;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
           int nv = meta.nvalid - HALF * h;
           nv = nv < 0 ? 0 : (nv > HALF ? HALF : nv);
           const int nk = (nv + 7) >> 3;
@@ -545,59 +592,55 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           tc_fence_after();
           tm.lap(t_aempty);
           unsigned char* bh = sm.B[h];
-          const uint32_t a_taddr = lane_taddr + A_COL + HALF * h;
-          if (ow < 2) {
-            float4* brow = reinterpret_cast<float4*>(bh + (uint32_t)(lane >> 3) * B_SBO + (uint32_t)(lane & 7) * 16u);
-#pragma unroll 2
-            for (int ks = 0; ks < nk; ++ks) {
-              const int c4 = (HALF * h + 8 * ks) >> 2;
-              const int4 ia = sidp[c4], ib = sidp[c4 + 1];
-              const float4 sa = featp[c4], sb = featp[c4 + 1];
-              float val[8];
-              val[0] = sa.x * jcp[ia.x * C]; val[1] = sa.y * jcp[ia.y * C];
-              val[2] = sa.z * jcp[ia.z * C]; val[3] = sa.w * jcp[ia.w * C];
-              val[4] = sb.x * jcp[ib.x * C]; val[5] = sb.y * jcp[ib.y * C];
-              val[6] = sb.z * jcp[ib.z * C]; val[7] = sb.w * jcp[ib.w * C];
-              uint32_t v[8];
+          // each half = two 32-pixel blocks; operand group g builds block g of the half: 32 row loads, one
+          // 32-column tcgen05.st (registers -> TMEM lanes), and for the h rows the K-major B tile
+          if (nv > 32 * ogrp) {
+            const int c0 = HALF * h + 32 * ogrp;  // first compacted pixel of the block
+            const uint32_t a_taddr = lane_taddr + A_COL + c0;
+            uint32_t v[32];
+            if (ow < 2) {
+              const float* src = vrow + c0 * C;
+              float val[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) val[j] = src[j * C];
               if (ow == 0) {
+                // B rows = features (this lane), 8 k-chunks of 4 pixels, 128 B apart
+                float4* brow = reinterpret_cast<float4*>(bh + (uint32_t)(lane >> 3) * B_SBO + (uint32_t)(lane & 7) * 16u) +
+                               8 * (8 * ogrp);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(val[j]);
-                brow[16 * ks] = make_float4(val[0], val[1], val[2], val[3]);      // k-chunk 2ks   (128 B apart)
-                brow[16 * ks + 8] = make_float4(val[4], val[5], val[6], val[7]);  // k-chunk 2ks+1
+                for (int q = 0; q < 8; ++q)
+                  brow[8 * q] = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(val[j]);
               } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(val[j] - tf32_trunc(val[j]));
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(val[j] - tf32_trunc(val[j]));
               }
-              tmem_st_x8(a_taddr + 8 * ks, v);
-            }
-          } else {
-            // pose / residual features: lanes 0-6 = h of feature 1+lane, lanes 7-13 = l of feature 1+(lane-7)
-            const int f = 1 + (lane < 7 ? lane : (lane < 14 ? lane - 7 : 0));
-            const float4* fp = featp + f * (TILE / 4);
-            const uint32_t brow_i = 32u + (uint32_t)(lane < 7 ? lane : 0);
-            float4* brow = reinterpret_cast<float4*>(bh + (brow_i >> 3) * B_SBO + (brow_i & 7u) * 16u);
-#pragma unroll 2
-            for (int ks = 0; ks < nk; ++ks) {
-              const int c4 = (HALF * h + 8 * ks) >> 2;
-              float val[8];
-              const float4 xa = fp[c4], xb = fp[c4 + 1];
-              val[0] = xa.x; val[1] = xa.y; val[2] = xa.z; val[3] = xa.w;
-              val[4] = xb.x; val[5] = xb.y; val[6] = xb.z; val[7] = xb.w;
+            } else {
+              // pose / residual features: lanes 0-6 = h of feature 1+lane, lanes 7-13 = l of feature 1+(lane-7)
+              const int f = 1 + (lane < 7 ? lane : (lane < 14 ? lane - 7 : 0));
+              const float4* fp = featp + f * (TILE / 4) + (c0 >> 2);
+              float4 x[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) x[q] = fp[q];
               if (lane < 7) {
-                brow[16 * ks] = xa;
-                brow[16 * ks + 8] = xb;
-              } else if (lane < 14) {
+                const uint32_t brow_i = 32u + (uint32_t)lane;
+                float4* brow = reinterpret_cast<float4*>(bh + (brow_i >> 3) * B_SBO + (brow_i & 7u) * 16u) + 8 * (8 * ogrp);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) val[j] = val[j] - tf32_trunc(val[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) val[j] = 0.0f;
+                for (int q = 0; q < 8; ++q) brow[8 * q] = x[q];
               }
-              uint32_t v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(val[j]);
-              tmem_st_x8(a_taddr + 8 * ks, v);
+              for (int q = 0; q < 8; ++q) {
+                float e0 = x[q].x, e1 = x[q].y, e2 = x[q].z, e3 = x[q].w;
+                if (lane >= 7) {
+                  e0 -= tf32_trunc(e0); e1 -= tf32_trunc(e1); e2 -= tf32_trunc(e2); e3 -= tf32_trunc(e3);
+                }
+                if (lane >= 14) { e0 = 0.f; e1 = 0.f; e2 = 0.f; e3 = 0.f; }
+                v[4 * q] = __float_as_uint(e0); v[4 * q + 1] = __float_as_uint(e1);
+                v[4 * q + 2] = __float_as_uint(e2); v[4 * q + 3] = __float_as_uint(e3);
+              }
             }
+            tmem_st_x32(a_taddr, v);
           }
           tm.lap(t_build);
           tmem_wait_st();
@@ -608,7 +651,10 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           tm.lap(t_sync);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.feat_empty[fb]);
+        if (lane == 0) {
+          mbar_arrive(&sm.feat_empty[fb]);
+          mbar_arrive(&sm.stage_empty[st]);
+        }
         tm.start();
 
         if (is_a && pend) {  // the chain that ended before this tile: its MMAs completed long ago

@@ -65,7 +65,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
         : "memory");
-    if (!ok) __nanosleep(128);
+    if (!ok) __nanosleep(400);
   }
 }
 

@@ -62,10 +62,10 @@ constexpr uint32_t B_HALF_BYTES = (NB / 8) * B_SBO;           // 12288 B
 constexpr int JC_STAGE_FLOATS = (TILE + 1) * C;               // +1: an all-zero row for padded pixels
 
 struct TileMeta {
-  int nvalid;
+  int nv[4];         // valid pixels of the four 32-pixel blocks (each block compacted on its own)
   int item_changed;
   int slot;
-  int pad;
+  int pad[2];
 };
 
 struct ItemSmem {
@@ -101,7 +101,6 @@ struct Smem {
   uint64_t d_empty[2];
   TileMeta meta[2];
   ItemSmem item[FE_GROUPS];
-  int cnt[FE_GROUPS][2][4];  // [group][tile parity within the group]: a fast warp may run one tile ahead of a slow one
   uint32_t tmem_base;
 };
 
@@ -211,21 +210,31 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c,
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 // ---- optional phase timers (clock64 sums per role), enabled with the env var DFK_TC_DEBUG=1 ----------
+// Compiled in only with -DDFK_TC_TIMERS (they cost ~40 instructions per tile and role).
 __device__ unsigned long long g_dbg[16];
+#ifdef DFK_TC_TIMERS
 struct Tmr {
   long long t;
   bool on;
   __device__ __forceinline__ void start() { if (on) t = clock64(); }
   __device__ __forceinline__ void lap(unsigned long long& acc) { if (on) { const long long n = clock64(); acc += (unsigned long long)(n - t); t = n; } }
 };
+#else
+struct Tmr {
+  long long t;
+  bool on;
+  __device__ __forceinline__ void start() {}
+  __device__ __forceinline__ void lap(unsigned long long&) {}
+};
+#endif
 
 // chain bookkeeping shared (by construction) between the control thread and the operand warps
 struct ChainState {
   int e = -1;              // current chain index
   int tiles_in_chain = 0;
-  __device__ __forceinline__ bool starts_chain(int i, const TileMeta& m) const
+  __device__ __forceinline__ bool starts_chain(int i, int item_changed) const
   {
-    return i == 0 || m.item_changed != 0 || tiles_in_chain == kFlushTiles;
+    return i == 0 || item_changed != 0 || tiles_in_chain == kFlushTiles;
   }
 };
 
@@ -292,29 +301,41 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       int it = 0;
       uint32_t tma_phase_bits = 0;
       int cur_item = -1;
+      uint32_t item_lo = 0, item_hi = 0;  // global tile range of the item in shared memory
+#ifdef DFK_TC_TIMERS
       Tmr tm{0, dbg != 0 && ft == 0};
+#else
+      Tmr tm{0, false};
+#endif
       unsigned long long t_tma = 0, t_geo = 0, t_fe_wait = 0, t_fe_write = 0, t_issue_fe = 0;
       for (int i = grp; i < ntiles; i += FE_GROUPS) {
         const int g = g_lo + i;
         const int st = i % STAGES;
         const int fb = grp;  // == i & 1
-        while ((uint32_t)g >= items[it].tile_begin + items[it].num_tiles) ++it;
-        // the tile sequence enters a new item here (relative to tile i-1, which the other group handles)
-        const bool seq_changed = (i == 0) || ((uint32_t)(g - 1) < items[it].tile_begin);
-        if (it != cur_item) {
+        if ((uint32_t)g >= item_hi || cur_item < 0) {
+          while ((uint32_t)g >= items[it].tile_begin + items[it].num_tiles) ++it;
           named_bar_sync(bar_id, FE_THREADS);
           load_item(I, items[it], ft, cta);
           cur_item = it;
           named_bar_sync(bar_id, FE_THREADS);
+          item_lo = I.tile_begin;
+          item_hi = I.tile_begin + I.num_tiles;
         }
-        const uint32_t k = (uint32_t)g - I.tile_begin;
-        const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
+        // the tile sequence enters a new item here (relative to tile i-1, which the other group handles)
+        const bool seq_changed = (i == 0) || ((uint32_t)(g - 1) < item_lo);
+        const uint32_t k = (uint32_t)g - item_lo;
+        const uint32_t tau = (k * I.perm_mul) % I.num_tiles;  // host guarantees k * perm_mul < 2^32
         const uint32_t p0 = tau * TILE;
         const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
         const bool bulk = (I.flags & ITEM_FLAG_BULK) != 0;
         const uint32_t s = ft;
-        const uint32_t px_lin = p0 + (s < n ? s : 0u);
-        const uint32_t py = px_lin / I.width, pxx = px_lin - py * I.width;
+        // tile origin (uniform) by one division, then this thread's pixel by wrap-around
+        const uint32_t y0 = p0 / I.width, x0 = p0 - y0 * I.width;
+        uint32_t pxx = x0 + (s < n ? s : 0u), py = y0;
+        while (pxx >= I.width) {
+          pxx -= I.width;
+          ++py;
+        }
         const float xn = __ldg(I.ray_tab + pxx);              // in flight while the tile lands
         const float yn = __ldg(I.ray_tab + I.width + py);
         tm.start();
@@ -322,12 +343,12 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           mbar_wait_parked(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
           tma_phase_bits ^= (1u << st);
         } else {
-          // stage st was last read by the operand warps of tile i-4, released before feat_empty(i-2) completed
+          // stage st was last read by the operand warps of tile i-4 (stage_empty / feat_empty completed)
           coop_tile_loads(sm, I, p0, n, st, ft);
           named_bar_sync(bar_id, FE_THREADS);
         }
-
         tm.lap(t_tma);
+
         float feat[8];
         bool ok = false;
         if (s < n) {
@@ -353,64 +374,63 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
             feat[7] = hw * diff;
           }
         }
+        // ---- warp-local compaction: this warp owns the 32-pixel block `fwarp` of the tile -----------
         const unsigned bal = __ballot_sync(0xffffffffu, ok);
         const int rank = __popc(bal & ((1u << lane) - 1u));
-        const int cpar = (i >> 1) & 1;
-        if (lane == 0) sm.cnt[grp][cpar][fwarp] = __popc(bal);
-        tm.lap(t_geo);
-        // feat[fb] / sid[fb] of tile i-2 must have been consumed; this also frees ring stage (i+2)%4
-        mbar_wait_parked(&sm.feat_empty[fb], ((i >> 1) & 1u) ^ 1u);
-        named_bar_sync(bar_id, FE_THREADS);
-        tm.lap(t_fe_wait);
-        int nvalid = 0, base = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < 4; ++w2) {
-          if (w2 == fwarp) base = nvalid;
-          nvalid += sm.cnt[grp][cpar][w2];
-        }
-        // In-place compaction of the staged code-Jacobian rows, scaled by s = w*e on the way:
-        // row c of the stage becomes the c-th VALID pixel's  s * jc[0..31]  (what the operand warps feed to
-        // the tensor core).  Rotated float4 order keeps both the reads (row = slot) and the writes
-        // (row = compacted index) free of bank conflicts.  A pixel never moves up (c <= slot), but rows are
-        // read by other threads than they are written by, hence the barrier between the two phases.
+        const int nvb = __popc(bal);
+        const int padded = (nvb + 7) & ~7;
+        // In-place compaction of the staged code-Jacobian rows of the block, scaled by s = w*e on the way:
+        // row 32*fwarp + r becomes the r-th VALID pixel's  s * jc[0..31]  (what the operand warps feed to the
+        // tensor core).  Rotated float4 order keeps reads (row = slot) and writes (row = rank) free of bank
+        // conflicts; all rows are read into registers before any is overwritten (same warp => __syncwarp).
         float4 rowv[C / 4];
         if (ok) {
-          const float4* src = reinterpret_cast<const float4*>(&sm.jc[st][s * C]);
+          // rows are 128-byte aligned: chunk (k4 ^ (lane & 7)) of row s  ==  (row address + (lane & 7) * 16) ^ (k4 * 16)
+          const uint32_t src = smem_u32(&sm.jc[st][s * C]) + ((uint32_t)(lane & 7) << 4);
 #pragma unroll
-          for (int k4 = 0; k4 < C / 4; ++k4) rowv[k4] = src[(k4 + lane) & (C / 4 - 1)];
+          for (int k4 = 0; k4 < C / 4; ++k4) {
+            const uint32_t addr = src ^ ((uint32_t)k4 << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(rowv[k4].x), "=f"(rowv[k4].y), "=f"(rowv[k4].z), "=f"(rowv[k4].w)
+                         : "r"(addr));
+          }
         }
-        named_bar_sync(bar_id, FE_THREADS);
+        __syncwarp();
+        tm.lap(t_geo);
+        // feat[fb] of tile i-2 must have been consumed by the operand warps
+        mbar_wait_parked(&sm.feat_empty[fb], ((i >> 1) & 1u) ^ 1u);
+        tm.lap(t_fe_wait);
+        const int blk0 = 32 * fwarp;
         if (ok) {
-          const int c = base + rank;
+          const int c = blk0 + rank;
           const float sc = feat[0];
-          float4* dst = reinterpret_cast<float4*>(&sm.jc[st][c * C]);
+          const uint32_t dst = smem_u32(&sm.jc[st][c * C]) + ((uint32_t)(lane & 7) << 4);
 #pragma unroll
           for (int k4 = 0; k4 < C / 4; ++k4) {
             const float4 v = rowv[k4];
-            dst[(k4 + lane) & (C / 4 - 1)] = make_float4(sc * v.x, sc * v.y, sc * v.z, sc * v.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst ^ ((uint32_t)k4 << 4)), "f"(sc * v.x),
+                         "f"(sc * v.y), "f"(sc * v.z), "f"(sc * v.w)
+                         : "memory");
           }
 #pragma unroll
           for (int f = 1; f < 8; ++f) sm.feat[fb][f][c] = feat[f];
         }
-        // pad the compacted list to a multiple of 8 with "pixels" that contribute exactly zero
-        if (ft < 8) {
-          const int c = nvalid + ft;
-          if (c < ((nvalid + 7) & ~7)) {
-            float4* dst = reinterpret_cast<float4*>(&sm.jc[st][c * C]);
+        // pad the block's list to a multiple of 8 with "pixels" that contribute exactly zero
+        if (lane < padded - nvb) {
+          const int c = blk0 + nvb + lane;
+          float4* dst = reinterpret_cast<float4*>(&sm.jc[st][c * C]);
 #pragma unroll
-            for (int k4 = 0; k4 < C / 4; ++k4) dst[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k4 = 0; k4 < C / 4; ++k4) dst[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int f = 1; f < 8; ++f) sm.feat[fb][f][c] = 0.0f;
-          }
+          for (int f = 1; f < 8; ++f) sm.feat[fb][f][c] = 0.0f;
         }
+        if (lane == 0) sm.meta[fb].nv[fwarp] = nvb;
         if (ft == 0) {
-          sm.meta[fb].nvalid = nvalid;
           sm.meta[fb].item_changed = seq_changed ? 1 : 0;
           sm.meta[fb].slot = (int)I.slot;
         }
         mbar_arrive(&sm.feat_full[fb]);
         tm.lap(t_fe_write);
-        tm.lap(t_issue_fe);
       }
       if (tm.on) {
         atomicAdd(&g_dbg[0], t_tma); atomicAdd(&g_dbg[1], t_geo); atomicAdd(&g_dbg[2], t_fe_wait);
@@ -422,7 +442,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         const uint32_t idesc = make_idesc_tf32(MM, NB);
         ChainState ch;
         bool first = true;
+#ifdef DFK_TC_TIMERS
         Tmr tm{0, dbg != 0};
+#else
+        Tmr tm{0, false};
+#endif
         unsigned long long t_afull = 0, t_issue = 0;
         for (int i = 0; i < ntiles; ++i) {
           const int fb = i & 1;
@@ -435,7 +459,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
             if (h == 0) {
               meta = sm.meta[fb];
               mbar_arrive(&sm.feat_empty[fb]);  // meta[fb] may now be overwritten (once the operand warps agree)
-              if (ch.starts_chain(i, meta)) {
+              if (ch.starts_chain(i, meta.item_changed)) {
                 if (i > 0) umma_commit(&sm.d_full[ch.e & 1]);
                 ch.e += 1;
                 ch.tiles_in_chain = 0;
@@ -448,15 +472,16 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
               }
               ch.tiles_in_chain += 1;
             }
-            int nv = meta.nvalid - HALF * h;
-            nv = nv < 0 ? 0 : (nv > HALF ? HALF : nv);
-            const int nk = (nv + 7) >> 3;
             const uint32_t d_addr = tbase + D_COL + NB * (ch.e & 1);
             const uint64_t bdesc0 = make_smem_desc_kmajor_noswizzle(smem_u32(sm.B[h]), 128, B_SBO);
-            for (int ks = 0; ks < nk; ++ks) {
-              umma_tf32_ts(d_addr, tbase + A_COL + HALF * h + 8 * ks, bdesc0 + (uint64_t)((ks * 256) >> 4), idesc,
-                           !first);
-              first = false;
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {  // the two 32-pixel blocks of the half
+              const int nk = (meta.nv[2 * h + bb] + 7) >> 3;
+              for (int ks = 0; ks < nk; ++ks) {
+                const int kc = 4 * bb + ks;  // 8-pixel k-step inside the half
+                umma_tf32_ts(d_addr, tbase + A_COL + HALF * h + 8 * kc, bdesc0 + (uint64_t)((kc * 256) >> 4), idesc, !first);
+                first = false;
+              }
             }
             umma_commit(&sm.a_empty[h]);
             tm.lap(t_issue);
@@ -542,10 +567,18 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         if (item_end && ow == 0 && lane == 0) reinterpret_cast<unsigned int*>(P)[kTcRows * kTcCols] = inl;
       };
 
+#ifdef DFK_TC_TIMERS
       Tmr tm{0, dbg != 0 && warp == 0 && lane == 0};
+#else
+      Tmr tm{0, false};
+#endif
       const bool is_a = (ogrp == 0);
       unsigned long long t_ffull = 0, t_aempty = 0, t_build = 0, t_sync = 0, t_drain = 0, t_total = 0;
+#ifdef DFK_TC_TIMERS
       const long long t_begin = tm.on ? clock64() : 0;
+#else
+      const long long t_begin = 0;
+#endif
       for (int i = 0; i < ntiles; ++i) {
         const int st = i % STAGES;
         const int fb = i & 1;
@@ -553,7 +586,8 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         mbar_wait(&sm.feat_full[fb], (i >> 1) & 1u);
         tm.lap(t_ffull);
         const TileMeta meta = sm.meta[fb];
-        if (is_a && ch.starts_chain(i, meta)) {
+        const int tile_valid = meta.nv[0] + meta.nv[1] + meta.nv[2] + meta.nv[3];
+        if (is_a && ch.starts_chain(i, meta.item_changed)) {
           if (i > 0) {
             pend = true;
             pend_e = ch.e;
@@ -574,8 +608,8 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           }
         }
         ch.tiles_in_chain += 1;
-        chain_valid += meta.nvalid;
-        inliers += (unsigned)meta.nvalid;
+        chain_valid += tile_valid;
+        inliers += (unsigned)tile_valid;
 
         // plain (non-volatile) shared-memory accesses: the compiler is free to overlap the loads of
         // several chunks; the mbarrier waits / fences around the loops carry the "memory" clobbers
@@ -583,9 +617,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         const float4* __restrict__ featp = reinterpret_cast<const float4*>(sm.feat[fb]);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          int nv = meta.nvalid - HALF * h;
-          nv = nv < 0 ? 0 : (nv > HALF ? HALF : nv);
-          const int nk = (nv + 7) >> 3;
+          const int nv = meta.nv[2 * h + ogrp];  // this group's block of the half
           // A/B half h was last read by the MMAs of tile i-1
           tm.start();
           mbar_wait(&sm.a_empty[h], (i & 1u) ^ 1u);
@@ -594,7 +626,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           unsigned char* bh = sm.B[h];
           // each half = two 32-pixel blocks; operand group g builds block g of the half: 32 row loads, one
           // 32-column tcgen05.st (registers -> TMEM lanes), and for the h rows the K-major B tile
-          if (nv > 32 * ogrp) {
+          if (nv > 0) {
             const int c0 = HALF * h + 32 * ogrp;  // first compacted pixel of the block
             const uint32_t a_taddr = lane_taddr + A_COL + c0;
             uint32_t v[32];
@@ -666,6 +698,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       if (is_a) drain(ch.e, chain_valid, cur_slot, slot_fresh, true, inliers);
       if (tm.on) {
         t_total = (unsigned long long)(clock64() - t_begin);
+        (void)t_begin;
         atomicAdd(&g_dbg[6], t_ffull); atomicAdd(&g_dbg[7], t_aempty); atomicAdd(&g_dbg[8], t_build);
         atomicAdd(&g_dbg[9], t_sync); atomicAdd(&g_dbg[10], t_drain); atomicAdd(&g_dbg[11], t_total);
         atomicAdd(&g_dbg[12], (unsigned long long)ntiles);

@@ -200,7 +200,7 @@ uint32_t gcd_u32(uint32_t a, uint32_t b)
 // stride for the in-item tile permutation: ~golden-ratio of the tile count, coprime with it
 uint32_t perm_multiplier(uint32_t n)
 {
-  if (n <= 2) return 1;
+  if (n <= 2 || n > 65535u) return 1;  // keeps k * perm_mul below 2^32 on the device
   uint32_t m = (uint32_t)((double)n * 0.6180339887498949);
   if (m < 1) m = 1;
   while (gcd_u32(m, n) != 1) ++m;
@@ -259,6 +259,8 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
     d.tile_begin = tile_cursor;
     tile_cursor += d.num_tiles;
     d.perm_mul = perm_multiplier(d.num_tiles);
+    d.mag_tiles = (uint32_t)((1ull << 32) / d.num_tiles);
+    d.mag_width = (uint32_t)((1ull << 32) / W);
     d.flags = 0;
     const bool bulk = (W % 4 == 0) && aligned(d.img0, 16) && aligned(d.dpt0, 16) && aligned(d.jac, 16) &&
                       (d.img0_pitch % 4 == 0) && (d.dpt0_pitch % 4 == 0) && (d.jac_pitch % 4 == 0) &&
@@ -334,7 +336,18 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
   if (!sfm_fp32_supported(code_size))
     return fail(h, DFK_ERR_UNSUPPORTED,
                 "[SfmAligner::RunStep] no kernel instantiated for code size " + std::to_string(code_size));
-  const bool tc = (h->gram_mode == DFK_GRAM_TF32X3) || (h->gram_mode == DFK_GRAM_AUTO && sfm_tc_supported(code_size));
+  bool tc = (h->gram_mode == DFK_GRAM_TF32X3) || (h->gram_mode == DFK_GRAM_AUTO && sfm_tc_supported(code_size));
+  if (tc) {
+    // the tensor-core kernel gathers grad1 with 8-byte loads; odd layouts go to the fp32 kernel (AUTO) or fail (forced)
+    bool grads_ok = true;
+    for (int i = 0; i < n && grads_ok; ++i)
+      grads_ok = items[i].grad1.ptr && aligned(items[i].grad1.ptr, 8) && (items[i].grad1.pitch_bytes % 8 == 0);
+    if (!grads_ok) {
+      if (h->gram_mode == DFK_GRAM_TF32X3)
+        return fail(h, DFK_ERR_UNSUPPORTED, "[SfmAligner::RunStep] tensor-core path needs 8-byte aligned grad1 rows");
+      tc = false;
+    }
+  }
   if (tc && !sfm_tc_supported(code_size))
     return fail(h, DFK_ERR_UNSUPPORTED,
                 "[SfmAligner::RunStep] tensor-core Gram path is not instantiated for code size " +

@@ -44,17 +44,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
   return ok != 0;
 }
 
-// A waiting warp must not monopolise its sub-core's issue port (the arbiter favours some warp ids):
-// back off with nanosleep between polls.
+// Waits use try_wait with a suspend-time hint: ptxas lowers it to SYNCS.PHASECHK + NANOSLEEP.SYNCS, a sleep
+// that the barrier's phase change wakes, so a waiting warp neither burns issue slots nor adds wake-up
+// latency (a plain spin loop was measured at ~35% of all issued instructions in the tensor-core kernel).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-  if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(40);
-}
-
-// Same, for long waits by a lone thread (MMA issuer): the suspend-time hint lets the hardware park the
-// thread until the phase completes instead of burning issue slots in a spin loop.
-__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
 {
   uint32_t ok = 0;
   while (!ok) {
@@ -65,9 +58,9 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity)
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
         : "memory");
-    if (!ok) __nanosleep(400);
   }
 }
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 
 // 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP); completes `bytes` of
 // transaction count on `bar`.  dst/src 16-byte aligned, bytes a multiple of 16.

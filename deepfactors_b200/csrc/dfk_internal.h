@@ -41,7 +41,9 @@ struct SfmItemDev {
   // tiling
   uint32_t tile_begin;  // first global tile index of this item
   uint32_t num_tiles;
-  uint32_t perm_mul;    // tile k of the item is processed as (k * perm_mul) % num_tiles
+  uint32_t perm_mul;    // tile k of the item is processed as (k * perm_mul) % num_tiles  (k * perm_mul < 2^32)
+  uint32_t mag_tiles;   // floor(2^32 / num_tiles): division by multiply-high + one correction step
+  uint32_t mag_width;   // floor(2^32 / width)
   // partial-sum bookkeeping: CTA c (first_cta <= c < first_cta+num_ctas) writes slot
   // partial_begin + (c - first_cta)
   uint32_t first_cta, num_ctas, partial_begin;
@@ -71,7 +73,10 @@ constexpr int kTcTilePixels = 128;  // tensor-core kernel
 // columns = B features (32 code, 7 pose/residual, 1 pad)
 constexpr int kTcRows = 78;
 constexpr int kTcCols = 40;
-constexpr int kTcPartialFloats = kTcRows * kTcCols + 8;
+// stored column-major with the row dimension padded to the 96 TMEM lanes of the three operand warps, so that a
+// warp's 32 lanes (rows) touch 32 consecutive floats per column: coalesced st / red
+constexpr int kTcRowsPad = 96;
+constexpr int kTcPartialFloats = kTcRowsPad * kTcCols + 8;
 
 struct SfmLaunchPlan {
   int num_items = 0;

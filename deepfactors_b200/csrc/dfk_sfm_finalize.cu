@@ -14,7 +14,7 @@
 //
 // Two partial formats:
 //   fp32 kernel : G itself, row-major NFP x NFP (features: code 0..C-1, a C..C+5, r C+6), upper blocks valid
-//   tcgen05     : D = [h rows ; l rows] x h columns (kTcRows x kTcCols);  G = HH + LH + LH^T
+//   tcgen05     : D = [h rows ; l rows] x h columns (kTcRows x kTcCols, stored column-major);  G = HH + LH + LH^T
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -45,7 +45,7 @@ sfm_finalize_kernel(const SfmItemDev* __restrict__ items, const float* __restric
   constexpr int NE = (C + 7 > 49) ? (C + 7) : 49;  // entries per unit (code row: <= C+7, pose unit: 49)
   constexpr int EPL = (NE + 31) / 32;              // entries per lane
   constexpr int PSTRIDE = TC ? kTcPartialFloats : Cfg::PARTIAL_FLOATS;
-  constexpr int INL_OFF = TC ? kTcRows * kTcCols : NFP * NFP;
+  constexpr int INL_OFF = TC ? kTcRowsPad * kTcCols : NFP * NFP;
   constexpr int NOFF = TC ? 3 : 1;
   __shared__ float red[kFinWarps][EPL * 32];
   __shared__ unsigned int red_inl[kFinWarps];
@@ -79,9 +79,9 @@ sfm_finalize_kernel(const SfmItemDev* __restrict__ items, const float* __restric
       fj = 0;
     }
     if constexpr (TC) {
-      off[q][0] = tc_hrow(fi) * kTcCols + fj;  // HH[i][j]
-      off[q][1] = tc_lrow(fi) * kTcCols + fj;  // LH[i][j]
-      off[q][2] = tc_lrow(fj) * kTcCols + fi;  // LH[j][i]
+      off[q][0] = fj * kTcRowsPad + tc_hrow(fi);  // HH[i][j]   (partials are column-major: [col][row])
+      off[q][1] = fj * kTcRowsPad + tc_lrow(fi);  // LH[i][j]
+      off[q][2] = fi * kTcRowsPad + tc_lrow(fj);  // LH[j][i]
     } else {
       off[q][0] = fi * NFP + fj;
     }

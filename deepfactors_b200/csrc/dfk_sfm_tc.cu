@@ -81,7 +81,7 @@ struct ItemSmem {
   const float* grad1;
   const float* ray_tab;
   uint32_t img0_pitch, img1_pitch, dpt0_pitch, valid0_pitch, jac_pitch, grad1_pitch;
-  uint32_t width, height, num_pixels, tile_begin, num_tiles, perm_mul, flags, slot;
+  uint32_t width, height, num_pixels, tile_begin, num_tiles, perm_mul, flags, slot, mag_tiles, mag_width;
 };
 
 struct Smem {
@@ -124,6 +124,8 @@ __device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, 
     dst.width = src.width; dst.height = src.height; dst.num_pixels = src.num_pixels;
     dst.tile_begin = src.tile_begin; dst.num_tiles = src.num_tiles; dst.perm_mul = src.perm_mul;
     dst.flags = src.flags;
+    dst.mag_tiles = src.mag_tiles;
+    dst.mag_width = src.mag_width;
     dst.slot = src.partial_begin + (uint32_t)cta - src.first_cta;
   }
 }
@@ -206,6 +208,18 @@ __device__ __forceinline__ int4 lds_i4(uint32_t addr)
 __device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d)
 {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// a / b and a % b through the precomputed mag = floor(2^32 / b): multiply-high, one correction step
+__device__ __forceinline__ uint32_t div_magic(uint32_t a, uint32_t b, uint32_t mag, uint32_t& rem)
+{
+  uint32_t q = __umulhi(a, mag);
+  uint32_t r = a - q * b;
+  if (r >= b) {
+    ++q;
+    r -= b;
+  }
+  rem = r;
+  return q;
 }
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
@@ -324,13 +338,15 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         // the tile sequence enters a new item here (relative to tile i-1, which the other group handles)
         const bool seq_changed = (i == 0) || ((uint32_t)(g - 1) < item_lo);
         const uint32_t k = (uint32_t)g - item_lo;
-        const uint32_t tau = (k * I.perm_mul) % I.num_tiles;  // host guarantees k * perm_mul < 2^32
+        uint32_t tau;
+        div_magic(k * I.perm_mul, I.num_tiles, I.mag_tiles, tau);  // host guarantees k * perm_mul < 2^32
         const uint32_t p0 = tau * TILE;
         const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
         const bool bulk = (I.flags & ITEM_FLAG_BULK) != 0;
         const uint32_t s = ft;
         // tile origin (uniform) by one division, then this thread's pixel by wrap-around
-        const uint32_t y0 = p0 / I.width, x0 = p0 - y0 * I.width;
+        uint32_t x0;
+        const uint32_t y0 = div_magic(p0, I.width, I.mag_width, x0);
         uint32_t pxx = x0 + (s < n ? s : 0u), py = y0;
         while (pxx >= I.width) {
           pxx -= I.width;
@@ -351,8 +367,20 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
 
         float feat[8];
         bool ok = false;
+#ifdef DFK_EXP_NOGEOM
+        if (s < n) {
+          ok = (s & 3u) != 0u;
+          const float d = sm.dpt0[st][s];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) feat[j] = 0.001f * (float)(j + 1) * d + xn * yn;
+          if (ok) I.valid0[(size_t)py * I.valid0_pitch + pxx] = 1.0f;
+        }
+        if (false) {
+          const uint32_t y = py, x = pxx;
+#else
         if (s < n) {
           const uint32_t y = py, x = pxx;
+#endif
           const float d = sm.dpt0[st][s];
           const Warped w = warp_ray(xn, yn, d, I.q, I.t, I.fx, I.fy, I.u0, I.v0, I.border, I.ulim, I.vlim, I.min_dpt);
           if (w.valid) {
@@ -361,7 +389,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
             int ix, iy;
             float fu, fv, gx, gy;
             bilin_setup(w.u, w.v, ix, iy, fu, fv);
-            sample_grad(I.grad1, I.grad1_pitch, (I.flags & ITEM_FLAG_GRAD_ALIGNED) != 0, ix, iy, fu, fv, gx, gy);
+            sample_grad(I.grad1, I.grad1_pitch, true, ix, iy, fu, fv, gx, gy);  // the API guarantees 8-byte rows here
             const float i1 = sample_scalar(I.img1, I.img1_pitch, ix, iy, fu, fv);
             float a[6], c00, c02, c11, c12;
             pose_jacobian_row(w, I.fx, I.fy, gx, gy, a, c00, c02, c11, c12);
@@ -527,7 +555,6 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       auto drain = [&](int e, int valid, int slot, bool fresh, bool item_end, unsigned int inl) {
         const int b = e & 1, use = e >> 1;
         float* P = partials + (size_t)slot * kTcPartialFloats;
-        const bool have_row = row < kTcRows;
         mbar_wait(&sm.d_full[b], use & 1u);
         tc_fence_after();
         // three passes of 16 accumulator columns keep the register footprint small.  The first chain of an
@@ -544,27 +571,25 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
               tmem_ld_x16(lane_taddr + D_COL + NB * b + 16 * pass, v);
               tmem_wait_ld();
             }
-            if (have_row) {
-              float* drow = P + row * kTcCols + 16 * pass;
-              if (fresh) {
+            // column-major partial: this lane's row at column j is P[j * kTcRowsPad + row] -> a warp writes 128
+            // contiguous bytes per column
+            float* dcol = P + (16 * pass) * kTcRowsPad + row;
+            if (fresh) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j < nq)
-                    __stcg(reinterpret_cast<float4*>(drow) + j,
-                           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-              } else {
+              for (int j = 0; j < 16; ++j)
+                if (j < 4 * nq) __stcg(dcol + j * kTcRowsPad, __uint_as_float(v[j]));
+            } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (j < 4 * nq) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(drow + j), "f"(__uint_as_float(v[j])) : "memory");
-              }
+              for (int j = 0; j < 16; ++j)
+                if (j < 4 * nq)
+                  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dcol + j * kTcRowsPad), "f"(__uint_as_float(v[j])) : "memory");
             }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.d_empty[b]);
-        if (item_end && ow == 0 && lane == 0) reinterpret_cast<unsigned int*>(P)[kTcRows * kTcCols] = inl;
+        if (item_end && ow == 0 && lane == 0) reinterpret_cast<unsigned int*>(P)[kTcRowsPad * kTcCols] = inl;
       };
 
 #ifdef DFK_TC_TIMERS
@@ -573,7 +598,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       Tmr tm{0, false};
 #endif
       const bool is_a = (ogrp == 0);
-      unsigned long long t_ffull = 0, t_aempty = 0, t_build = 0, t_sync = 0, t_drain = 0, t_total = 0;
+      unsigned long long t_ffull = 0, t_aempty = 0, t_build = 0, t_sync = 0, t_drain = 0, t_total = 0, t_misc = 0;
 #ifdef DFK_TC_TIMERS
       const long long t_begin = tm.on ? clock64() : 0;
 #else
@@ -613,6 +638,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
 
         // plain (non-volatile) shared-memory accesses: the compiler is free to overlap the loads of
         // several chunks; the mbarrier waits / fences around the loops carry the "memory" clobbers
+        tm.lap(t_misc);
         const float* __restrict__ vrow = sm.jc[st] + lane;  // compacted, pre-scaled rows: vrow[c * C]
         const float4* __restrict__ featp = reinterpret_cast<const float4*>(sm.feat[fb]);
 #pragma unroll 1
@@ -701,7 +727,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         (void)t_begin;
         atomicAdd(&g_dbg[6], t_ffull); atomicAdd(&g_dbg[7], t_aempty); atomicAdd(&g_dbg[8], t_build);
         atomicAdd(&g_dbg[9], t_sync); atomicAdd(&g_dbg[10], t_drain); atomicAdd(&g_dbg[11], t_total);
-        atomicAdd(&g_dbg[12], (unsigned long long)ntiles);
+        atomicAdd(&g_dbg[12], (unsigned long long)ntiles); atomicAdd(&g_dbg[14], t_misc);
       }
     }
   }
@@ -753,9 +779,9 @@ cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan
     fprintf(stderr,
             "[dfk tc dbg] ctas=%d tiles=%d | per tile cycles: FE(g0+g1 thread0) tma_wait %.0f geom %.0f feat_empty_wait %.0f "
             "write %.0f tma_issue %.0f | CTRL a_full_wait %.0f issue %.0f | OP feat_full_wait %.0f a_empty_wait %.0f build %.0f sync %.0f "
-            "drain %.0f total %.0f\n",
+            "drain %.0f misc %.0f total %.0f\n",
             plan.num_ctas, plan.num_tiles, v[0] / nt, v[1] / nt, v[2] / nt, v[3] / nt, v[13] / nt, v[4] / nt, v[5] / nt, v[6] / nt,
-            v[7] / nt, v[8] / nt, v[9] / nt, v[10] / nt, v[11] / nt);
+            v[7] / nt, v[8] / nt, v[9] / nt, v[10] / nt, v[14] / nt, v[11] / nt);
   }
   return cudaGetLastError();
 }

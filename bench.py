@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=8)
     ap.add_argument("--gram", default="auto", choices=["auto", "fp32", "tf32x3"])
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -291,16 +291,24 @@ def main():
     for s in stage:
         s["valid0"] = torch.zeros_like(s["img0"])
     h2d = sum(v.numel() * 4 for hl in pinned for v in hl.values())
-    d2h = LEVELS * (rec_floats - 1) * 4 + LEVELS * 8
+    d2h = LEVELS * rec_floats * 4
+
+    e2e_items = [dict(pose0=base.pose0, pose1=base.pose1, cam=L.cam, img0=sd["img0"], img1=sd["img1"], dpt0=sd["dpt0"],
+                      valid0=sd["valid0"], prx0_jac=sd["prx0_jac"], grad1=sd["grad1"]) for L, sd in zip(base.levels, stage)]
+    e2e_work = al.make_work_items(e2e_items)
+    e2e_rec_dev = torch.empty((LEVELS, rec_floats), dtype=torch.float32, device=dev)
+    e2e_rec_host = torch.empty((LEVELS, rec_floats), dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        out = []
-        for L, hp, sd in zip(base.levels, pinned, stage):
+        # every input of the evaluation travels host -> device (pinned, async on the launch stream), one batched
+        # C-ABI launch evaluates the 4 levels, the 4 result records travel back and the host waits for them
+        for hp, sd in zip(pinned, stage):
             for k, v in hp.items():
                 sd[k].copy_(v, non_blocking=True)
-            out.append(al.RunStep(base.pose0, base.pose1, base.code, L.cam, sd["img0"], sd["img1"], sd["dpt0"], None,
-                                  sd["valid0"], sd["prx0_jac"], sd["grad1"]))
-        return out
+        al.RunStepBatch(e2e_work, e2e_rec_dev)
+        e2e_rec_host.copy_(e2e_rec_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return e2e_rec_host
 
     e2e_step()
     torch.cuda.synchronize()
@@ -323,6 +331,10 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         bytes_per_launch = P * BYTES_PER_EVAL
+        traffic = None  # dram__bytes_read+write of one step-kernel launch, from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and P == 8 and args.gram in ("auto", "tf32x3"):
+            traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = bytes_per_launch / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
         single["frac_of_hbm_roofline"] = (BYTES_PER_EVAL / (single_ms * 1e-3) / 1e9) / peak
@@ -342,14 +354,15 @@ def main():
                        "parallelism": f"pairs sharded over {n_gpus} GPU(s)" + (
                            "; one NCCL all-reduce of the window's normal equations per step" if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "kernel": "sfm_step kernel (per-tile warp + Gram)", "launches_timed": kern_n,
                          "avg_launch_ms": kern_avg_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps, "note": "per step: every level's img0/img1/dpt0/prx_jac/grad1 copied "
-                    "from pinned host memory, 4 synchronous dfk_sfm_run_step calls, results returned by value"},
+                    "from pinned host memory (async, launch stream), one dfk_sfm_run_step_batch call for the 4 levels, "
+                    "the 4 result records copied back and waited for"},
             "single_launch": single,
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--code-sigma", type=float, default=0.0,
+                    help="std of the latent code used to decode dpt0 (0 = the reference test's zero code, smooth depth; "
+                         ">0 adds per-pixel depth noise through the iid synthetic code Jacobian)")
+    ap.add_argument("--identity-pose", action="store_true", help="100%% inliers (worst-case work) instead of the ~60%% of the reference test poses")
     return ap.parse_args()
 
 
@@ -192,7 +196,7 @@ def main():
 
     P = args.pairs_per_step
     # ---- synthetic window: P distinct pairs resident in HBM -------------------------------------------
-    base = synth.make_pair(W0, H0, CS, LEVELS, seed=rank, code_sigma=0.5)
+    base = synth.make_pair(W0, H0, CS, LEVELS, seed=rank, code_sigma=args.code_sigma, identity_pose=args.identity_pose)
     host_levels = []
     for L in base.levels:
         host_levels.append(dict(img0=L.img0, img1=L.img1, dpt0=L.dpt0, prx0_jac=L.prx_jac, grad1=L.grad1))
@@ -349,6 +353,9 @@ def main():
                                    f"{P} distinct pairs per step in one persistent launch",
                        "evals_per_step_per_gpu": P, "pixels_per_eval": PIXELS,
                        "algorithmic_bytes_per_eval": BYTES_PER_EVAL, "gram": args.gram,
+                       "poses": "identity (100% inliers)" if args.identity_pose else
+                                "tests/ut_sfmaligner.cpp:254-264 (~60% inliers)",
+                       "code_sigma": args.code_sigma,
                        "l2": f"inputs larger than L2: each step streams {P * BYTES_PER_EVAL / 1e6:.0f} MB of distinct "
                              "pair data (> 126 MB L2)",
                        "parallelism": f"pairs sharded over {n_gpus} GPU(s)" + (

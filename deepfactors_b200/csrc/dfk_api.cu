@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -200,6 +201,8 @@ uint32_t gcd_u32(uint32_t a, uint32_t b)
 // stride for the in-item tile permutation: ~golden-ratio of the tile count, coprime with it
 uint32_t perm_multiplier(uint32_t n)
 {
+  static const bool no_perm = []() { const char* e = getenv("DFK_NO_PERM"); return e && e[0] == '1'; }();
+  if (no_perm) return 1;
   if (n <= 2 || n > 65535u) return 1;  // keeps k * perm_mul below 2^32 on the device
   uint32_t m = (uint32_t)((double)n * 0.6180339887498949);
   if (m < 1) m = 1;

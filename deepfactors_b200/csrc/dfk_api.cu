@@ -336,7 +336,8 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
 {
   if (!h) return DFK_ERR_INVALID_ARG;
   if (!items || n <= 0 || !records_dev) return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] null/empty batch");
-  if (!sfm_fp32_supported(code_size))
+  const bool wide = sfm_wide_supported(code_size);
+  if (!sfm_fp32_supported(code_size) && !wide)
     return fail(h, DFK_ERR_UNSUPPORTED,
                 "[SfmAligner::RunStep] no kernel instantiated for code size " + std::to_string(code_size));
   bool tc = (h->gram_mode == DFK_GRAM_TF32X3) || (h->gram_mode == DFK_GRAM_AUTO && sfm_tc_supported(code_size));
@@ -362,7 +363,8 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     for (int i = 0; i < n; ++i) ray_floats += (size_t)items[i].img0.width + items[i].img0.height;
     DFK_CUDA(h, ensure(&h->ray_tabs_dev, &h->ray_tabs_cap, ray_floats), "[SfmAligner::RunStep] scratch allocation failed");
   }
-  DfkStatus st = build_items(h, items, n, code_size, tc ? kTcTilePixels : kTilePixels, tc ? 2 * h->num_sms : h->num_sms,
+  const int tile_px = tc ? kTcTilePixels : (wide ? sfm_wide_tile_pixels(code_size) : kTilePixels);
+  DfkStatus st = build_items(h, items, n, code_size, tile_px, tc ? 2 * h->num_sms : h->num_sms,
                              tc ? h->ray_tabs_dev : nullptr, &plan);
   if (st != DFK_OK) return st;
   const size_t pfloats = tc ? (size_t)kTcPartialFloats : sfm_partial_floats(code_size);
@@ -381,6 +383,9 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     DFK_CUDA(h, launch_sfm_tc(h->items_dev, plan, h->ray_tabs_dev, h->partials_dev, h->stream, ev0, ev1),
              "[SfmAligner::RunStep] kernel launch failed");
     h->launches += 1;  // ray-table kernel
+  } else if (wide) {
+    DFK_CUDA(h, launch_sfm_wide(code_size, h->items_dev, plan, h->partials_dev, h->stream, ev0, ev1),
+             "[SfmAligner::RunStep] kernel launch failed");
   } else {
     DFK_CUDA(h, launch_sfm_fp32(code_size, h->items_dev, plan, h->partials_dev, records_dev, h->stream, ev0, ev1),
              "[SfmAligner::RunStep] kernel launch failed");
@@ -410,7 +415,10 @@ const char* dfk_status_string(DfkStatus s)
   return "unknown";
 }
 
-int dfk_sfm_supports_code_size(int code_size) { return sfm_fp32_supported(code_size) ? 1 : 0; }
+int dfk_sfm_supports_code_size(int code_size)
+{
+  return (sfm_fp32_supported(code_size) || sfm_wide_supported(code_size)) ? 1 : 0;
+}
 
 DfkStatus dfk_create(int device, DfkHandle* out)
 {

@@ -92,6 +92,12 @@ cudaError_t launch_sfm_fp32(int code_size, const SfmItemDev* items_dev, const Sf
                             cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr);
 cudaError_t launch_sfm_finalize(int code_size, bool tc, const SfmItemDev* items_dev, int num_items,
                                 const float* partials_dev, float* records_dev, cudaStream_t stream);
+// dfk_sfm_wide.cu : C = 64 / 128 (thread-owned 8x8 blocks); partial format = the fp32 kernel's
+constexpr int sfm_wide_tile_pixels(int code_size) { return code_size >= 128 ? 64 : 128; }
+bool sfm_wide_supported(int code_size);
+cudaError_t launch_sfm_wide(int code_size, const SfmItemDev* items_dev, const SfmLaunchPlan& plan,
+                            float* partials_dev, cudaStream_t stream, cudaEvent_t ev_start = nullptr,
+                            cudaEvent_t ev_stop = nullptr);
 // dfk_sfm_tc.cu
 bool sfm_tc_supported(int code_size);
 cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, float* ray_tabs_dev,

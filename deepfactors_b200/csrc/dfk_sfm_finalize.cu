@@ -202,6 +202,8 @@ cudaError_t launch_sfm_finalize(int code_size, bool tc, const SfmItemDev* items_
     case 8: return launch_fin<8, false>(items_dev, num_items, partials_dev, records_dev, stream);
     case 16: return launch_fin<16, false>(items_dev, num_items, partials_dev, records_dev, stream);
     case 32: return launch_fin<32, false>(items_dev, num_items, partials_dev, records_dev, stream);
+    case 64: return launch_fin<64, false>(items_dev, num_items, partials_dev, records_dev, stream);
+    case 128: return launch_fin<128, false>(items_dev, num_items, partials_dev, records_dev, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -437,6 +437,8 @@ size_t sfm_partial_floats(int code_size)
     case 8: return SfmCfg<8>::PARTIAL_FLOATS;
     case 16: return SfmCfg<16>::PARTIAL_FLOATS;
     case 32: return SfmCfg<32>::PARTIAL_FLOATS;
+    case 64: return SfmCfg<64>::PARTIAL_FLOATS;
+    case 128: return SfmCfg<128>::PARTIAL_FLOATS;
     default: return 0;
   }
 }

@@ -155,29 +155,6 @@ __device__ __forceinline__ void issue_tile_loads(Smem& sm, const SfmItemDev* __r
   }
 }
 
-// Same, from the front-end group's shared-memory copy of the item (no global loads, 32-bit arithmetic).
-__device__ __forceinline__ void issue_tile_loads_smem(Smem& sm, const ItemSmem& I, int g, int st)
-{
-  const uint32_t k = (uint32_t)g - I.tile_begin;
-  const uint32_t tau = (k * I.perm_mul) % I.num_tiles;  // host guarantees k * perm_mul < 2^32
-  const uint32_t p0 = tau * TILE;
-  const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
-  const uint32_t W = I.width;
-  uint32_t y = p0 / W;
-  uint32_t x = p0 - y * W;
-  mbar_arrive_expect_tx(&sm.tma_full[st], n * (C + 2) * 4u);
-  uint32_t slot = 0;
-  while (slot < n) {
-    const uint32_t seg = min(W - x, n - slot);
-    bulk_g2s(&sm.jc[st][slot * C], I.jac + (size_t)y * I.jac_pitch + (size_t)x * C, seg * C * 4u, &sm.tma_full[st]);
-    bulk_g2s(&sm.img0[st][slot], I.img0 + (size_t)y * I.img0_pitch + x, seg * 4u, &sm.tma_full[st]);
-    bulk_g2s(&sm.dpt0[st][slot], I.dpt0 + (size_t)y * I.dpt0_pitch + x, seg * 4u, &sm.tma_full[st]);
-    slot += seg;
-    x = 0;
-    ++y;
-  }
-}
-
 __device__ __forceinline__ void coop_tile_loads(Smem& sm, const ItemSmem& I, uint32_t p0, uint32_t n, int st, int ft)
 {
   const uint32_t W = I.width;
@@ -195,22 +172,6 @@ __device__ __forceinline__ void coop_tile_loads(Smem& sm, const ItemSmem& I, uin
   }
 }
 
-__device__ __forceinline__ float4 lds_f4(uint32_t addr)
-{
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ int4 lds_i4(uint32_t addr)
-{
-  int4 v;
-  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d)
-{
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 // a / b and a % b through the precomputed mag = floor(2^32 / b): multiply-high, one correction step
 __device__ __forceinline__ uint32_t div_magic(uint32_t a, uint32_t b, uint32_t mag, uint32_t& rem)
 {

@@ -39,6 +39,7 @@ def test_non_compute_calls_work_without_a_gpu():
     assert L.dfk_version() == 100
     assert L.dfk_status_string(0) == b"ok"
     assert L.dfk_sfm_supports_code_size(32) == 1
+    assert L.dfk_sfm_supports_code_size(64) == 1 and L.dfk_sfm_supports_code_size(128) == 1
     assert L.dfk_sfm_supports_code_size(5) == 0
     assert _lib.record_floats(32) == 990 + 44 + 2
 

@@ -74,6 +74,41 @@ def test_full_size_properties(full_pair, mode):
         assert ev.inliers >= full.inliers and ev.residual >= 0.999 * full.residual
 
 
+def test_c128_full_size_properties():
+    """BASELINE config (v): 640x480, C=128 (thread-owned-block kernel): reproducible, additive, inliers == mask"""
+    import torch
+    from deepfactors_b200.aligners import SfmAligner
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    pair = synth.make_pair(640, 480, 128, 1, seed=4)
+    L = pair.levels[0]
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in dict(
+        img0=L.img0, img1=L.img1, dpt0=L.dpt0, prx0_jac=L.prx_jac, grad1=L.grad1).items()}
+    d["valid0"] = torch.zeros_like(d["img0"])
+    d["cam"] = L.cam
+    al = SfmAligner(128)
+    full, again = run(al, pair, d), run(al, pair, d)
+    assert np.array_equal(full.JtJ, again.JtJ) and full.residual == again.residual, "not reproducible"
+    assert full.inliers == int((d["valid0"] == 1).sum()) and full.inliers > 100000
+    top, bot = d["dpt0"].clone(), d["dpt0"].clone()
+    top[240:] = -1.0
+    bot[:240] = -1.0
+    a, b = run(al, pair, d, top), run(al, pair, d, bot)
+    assert a.inliers + b.inliers == full.inliers
+    scale = np.abs(full.JtJ).max()
+    assert np.abs((a.JtJ + b.JtJ) - full.JtJ).max() <= 2e-5 * scale
+    assert np.abs((a.Jtr + b.Jtr) - full.Jtr).max() <= 1e-4 * np.abs(full.Jtr).max()
+    H = full.toDenseMatrix()
+    assert H.shape == (140, 140) and np.allclose(H, H.T)
+    # the 32 leading code columns of a C=128 evaluation == a C=32 evaluation on the same leading Jacobian slices
+    d32 = dict(d)
+    d32["prx0_jac"] = d["prx0_jac"][:, :, :32].contiguous()
+    al32 = SfmAligner(32, gram_mode="fp32")
+    sub = run(al32, pair, d32)
+    assert sub.inliers == full.inliers
+    assert np.abs(sub.toDenseMatrix() - H[:44, :44]).max() <= 2e-5 * scale
+
+
 def test_gram_engines_agree_on_the_full_pyramid(full_pair):
     from deepfactors_b200.aligners import SfmAligner
     pair, dev = full_pair

@@ -54,6 +54,11 @@ class DfkSfmWorkItem(C.Structure):
                 ("prx0_jac", DfkImage), ("grad1", DfkImage)]
 
 
+class DfkTrackLevel(C.Structure):
+    _fields_ = [("cam", DfkCamera), ("img0", DfkImage), ("img1", DfkImage), ("dpt0", DfkImage), ("grad1", DfkImage),
+                ("iterations", C.c_int)]
+
+
 # every symbol include/dfk.h declares: (name, restype, argtypes)
 _F = C.POINTER(C.c_float)
 _IMG = C.POINTER(DfkImage)
@@ -83,6 +88,7 @@ SYMBOLS = {
     "dfk_sfm_run_step_batch": (C.c_int, [_H, C.POINTER(DfkSfmWorkItem), C.c_int, C.c_int, C.c_void_p]),
     "dfk_sfm_run_step_batch_host": (C.c_int, [_H, C.POINTER(DfkSfmWorkItem), C.c_int, C.c_int, _F]),
     "dfk_se3_run_step": (C.c_int, [_H, _F, _CAM, _IMG, _IMG, _IMG, _IMG, _F, _F, _F, C.POINTER(C.c_uint64)]),
+    "dfk_se3_track": (C.c_int, [_H, _F, C.POINTER(DfkTrackLevel), C.c_int, _F, _F, _F, _F, C.c_int]),
     "dfk_se3_warp": (C.c_int, [_H, _F, _CAM, _IMG, _IMG, _IMG, _IMG, _F, C.POINTER(C.c_uint64)]),
     "dfk_update_depth": (C.c_int, [_H, _F, C.c_int, _IMG, _IMG, C.c_float, _IMG]),
     "dfk_sobel_gradients": (C.c_int, [_H, _IMG, _IMG]),

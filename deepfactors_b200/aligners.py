@@ -23,7 +23,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DfkCamera, DfkDenseSfmParams, DfkImage, DfkSfmAlignerParams, DfkSfmWorkItem, check, lib
+from ._lib import (DfkCamera, DfkDenseSfmParams, DfkImage, DfkSfmAlignerParams, DfkSfmWorkItem, DfkTrackLevel, check,
+                   lib)
 
 
 # ------------------------------------------------------------------------------------------- params
@@ -285,6 +286,88 @@ class SE3Aligner:
                                 C.byref(i2), C.byref(res), C.byref(inl))
         check(self._hd.h, st)
         return CorrespondenceReductionItem(float(res.value), int(inl.value))
+
+
+# ------------------------------------------------------------------------------------------- CameraTracker
+@dataclass
+class TrackerConfig:
+    """CameraTracker::TrackerConfig (core/system/camera_tracker.h:45-50)"""
+    pyramid_levels: int = 3
+    iterations_per_level: Sequence[int] = (10, 5, 4)   # index = pyramid level, 0 = finest
+    huber_delta: float = 0.1
+
+
+class CameraTracker:
+    """df::CameraTracker (core/system/camera_tracker.{h,cpp}), the part that touches the GPU: TrackFrame's
+    coarse-to-fine Gauss-Newton on pose_ck.  The reference synchronises and solves on the host after every SE3 step
+    (camera_tracker.cpp:53-63); here the whole loop is enqueued at once (dfk_se3_track) and the 6x6 solve + retraction
+    run in the last block of every step kernel.  Keyframe bookkeeping (SetKeyframe / GetPoseEstimate pose algebra,
+    camera_tracker.cpp:94-121) is host-side and kept as plain methods."""
+
+    def __init__(self, camera_pyr, config: TrackerConfig, device=None):
+        if len(config.iterations_per_level) != config.pyramid_levels:
+            # the reference LOG(FATAL)s here (camera_tracker.cpp:32-33)
+            raise ValueError("CameraTracker config error: iterations_per_level size not equal pyramid_levels")
+        self.config_ = config
+        self.camera_pyr_ = list(camera_pyr)
+        self._hd = _Handle(device)
+        check(self._hd.h, lib().dfk_se3_set_huber_delta(self._hd.h, C.c_float(config.huber_delta)))
+        self.pose_ck_ = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float32)
+        self.kf_ = None
+        self.inliers_ = 0.0
+        self.error_ = float("inf")
+        self.history_ = None
+
+    def Reset(self):
+        self.pose_ck_ = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float32)
+
+    def SetKeyframe(self, kf_pyr_img, kf_pyr_dpt, pose_wk=None):
+        """kf_pyr_img / kf_pyr_dpt: per-level keyframe image and depth (level 0 = finest)"""
+        from . import se3 as _se3
+        if self.kf_ is not None and pose_wk is not None and self.kf_[2] is not None:
+            wc = _se3.compose(self.kf_[2], _se3.inverse(self.pose_ck_))
+            self.pose_ck_ = _se3.compose(_se3.inverse(wc), pose_wk).astype(np.float32)
+        self.kf_ = (list(kf_pyr_img), list(kf_pyr_dpt), None if pose_wk is None else np.asarray(pose_wk, np.float32))
+
+    def GetPoseEstimate(self):
+        from . import se3 as _se3
+        pose_wk = self.kf_[2] if self.kf_[2] is not None else np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float32)
+        return _se3.compose(pose_wk, _se3.inverse(self.pose_ck_))
+
+    def GetInliers(self) -> float:
+        return self.inliers_
+
+    def GetError(self) -> float:
+        return self.error_
+
+    def TrackFrame(self, pyr_img1, pyr_grad1, keep_history: bool = False):
+        if self.kf_ is None:
+            raise RuntimeError("Calling CameraTracker::TrackFrame before a keyframe was set")
+        self._hd.use_torch_stream()
+        n = self.config_.pyramid_levels
+        levels = (DfkTrackLevel * n)()
+        for l in range(n):
+            levels[l].cam = _cam(self.camera_pyr_[l])
+            levels[l].img0 = _image(self.kf_[0][l])
+            levels[l].img1 = _image(pyr_img1[l])
+            levels[l].dpt0 = _image(self.kf_[1][l])
+            levels[l].grad1 = _image(pyr_grad1[l], 2)
+            levels[l].iterations = int(self.config_.iterations_per_level[l])
+        total = int(sum(self.config_.iterations_per_level))
+        pose = np.ascontiguousarray(self.pose_ck_, dtype=np.float32).copy()
+        frac, err = C.c_float(0), C.c_float(0)
+        last = np.zeros(29, dtype=np.float32)
+        hist = np.zeros((max(total, 1), 36), dtype=np.float32) if keep_history else None
+        F = C.POINTER(C.c_float)
+        st = lib().dfk_se3_track(self._hd.h, pose.ctypes.data_as(F), levels, n, C.byref(frac), C.byref(err),
+                                 last.ctypes.data_as(F), hist.ctypes.data_as(F) if keep_history else None,
+                                 total if keep_history else 0)
+        check(self._hd.h, st)
+        self.pose_ck_ = pose
+        self.inliers_ = float(frac.value)
+        self.error_ = float(err.value)
+        self.history_ = hist[:total] if keep_history else None
+        return pose
 
 
 # ------------------------------------------------------------------------------------------- free functions

@@ -33,6 +33,10 @@ struct DfkContext {
   float* out_dev = nullptr;          // 32 floats
   float* out_host = nullptr;         // pinned, 32 floats
   float* code_dev = nullptr;         // 256 floats
+  float* track_dev = nullptr;        // dfk_se3_track: [pose 8 | per-iteration history 36 each]
+  size_t track_cap = 0;              // floats
+  float* track_host = nullptr;       // pinned mirror of track_dev + the last system (32)
+  size_t track_host_cap = 0;
 
   SfmItemDev* items_dev = nullptr;
   size_t items_cap = 0;
@@ -461,6 +465,8 @@ DfkStatus dfk_destroy(DfkHandle h)
   DeviceGuard guard(h->device);
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   cudaFree(h->simple_scratch); cudaFree(h->counter); cudaFree(h->out_dev); cudaFree(h->code_dev);
+  cudaFree(h->track_dev);
+  if (h->track_host) cudaFreeHost(h->track_host);
   cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev); cudaFree(h->ray_tabs_dev);
   if (h->out_host) cudaFreeHost(h->out_host);
   if (h->records_host) cudaFreeHost(h->records_host);
@@ -678,6 +684,76 @@ DfkStatus dfk_se3_run_step(DfkHandle h, const float se3[7], const DfkCamera* cam
   uint32_t bits;
   memcpy(&bits, &h->out_host[28], 4);
   *inliers = bits;
+  return DFK_OK;
+}
+
+DfkStatus dfk_se3_track(DfkHandle h, float pose_ck[7], const DfkTrackLevel* levels, int num_levels,
+                        float* inlier_fraction, float* error, float* last_system, float* history, int history_capacity)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!pose_ck || !levels || num_levels <= 0)
+    return fail(h, DFK_ERR_INVALID_ARG, "[CameraTracker::TrackFrame] null argument / no pyramid levels");
+  int total_iters = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const DfkTrackLevel& L = levels[l];
+    const uint32_t W = L.img0.width, H = L.img0.height;
+    if (L.iterations < 0 || W == 0 || H == 0 || !img_ok(&L.img0, W, H, 1) || !img_ok(&L.img1, W, H, 1) ||
+        !img_ok(&L.dpt0, W, H, 1) || !img_ok(&L.grad1, W, H, 2))
+      return fail(h, DFK_ERR_INVALID_ARG,
+                  "[CameraTracker::TrackFrame] inconsistent image views / negative iteration count at level " +
+                      std::to_string(l));
+    total_iters += L.iterations;
+  }
+  if (history && history_capacity < total_iters)
+    return fail(h, DFK_ERR_INVALID_ARG, "[CameraTracker::TrackFrame] history buffer too small");
+  DeviceGuard guard(h->device);
+  const size_t nfloat = 8 + 36 * (size_t)std::max(total_iters, 1);
+  DFK_CUDA(h, ensure(&h->track_dev, &h->track_cap, nfloat), "[CameraTracker::TrackFrame] scratch allocation failed");
+  if (h->track_host_cap < nfloat + 32) {
+    if (h->track_host) cudaFreeHost(h->track_host);
+    h->track_host = nullptr;
+    h->track_host_cap = 0;
+    DFK_CUDA(h, cudaMallocHost((void**)&h->track_host, sizeof(float) * (nfloat + 32)),
+             "[CameraTracker::TrackFrame] pinned allocation failed");
+    h->track_host_cap = nfloat + 32;
+  }
+  // the pose goes to the device once; every iteration reads it there and its last block writes the update
+  memcpy(h->track_host, pose_ck, sizeof(float) * 7);
+  DFK_CUDA(h, cudaMemcpyAsync(h->track_dev, h->track_host, sizeof(float) * 7, cudaMemcpyHostToDevice, h->stream),
+           "[CameraTracker::TrackFrame] pose upload failed");
+  DFK_CUDA(h, cudaMemsetAsync(h->out_dev, 0, sizeof(float) * 32, h->stream), "[CameraTracker::TrackFrame] memset failed");
+  int it = 0;
+  uint32_t last_area = 0;
+  for (int l = num_levels - 1; l >= 0; --l) {  // coarse to fine (camera_tracker.cpp:48)
+    const DfkTrackLevel& L = levels[l];
+    const PixelCam pc = make_pixel_cam(pose_ck, &L.cam, 1, 0.0f);  // q/t are overridden by the device pose
+    const View g = view_of(&L.grad1);
+    const bool galigned = aligned(g.ptr, 8) && g.pitch % 2 == 0;
+    for (int k = 0; k < L.iterations; ++k, ++it) {
+      DFK_CUDA(h, launch_se3_step(pc, h->se3_huber_delta, (int)L.img0.width, (int)L.img0.height, view_of(&L.img0),
+                                  view_of(&L.img1), view_of(&L.dpt0), g, galigned, h->simple_scratch, h->counter,
+                                  h->out_dev, h->stream, h->track_dev, h->track_dev + 8 + 36 * (size_t)it),
+               "[CameraTracker::TrackFrame] kernel launch failed");
+      h->launches += 1;
+      last_area = L.img0.width * L.img0.height;
+    }
+  }
+  // one read-back: final pose, the last evaluated system, the per-iteration history
+  float* host_sys = h->track_host + nfloat;
+  DFK_CUDA(h, cudaMemcpyAsync(h->track_host, h->track_dev, sizeof(float) * (8 + 36 * (size_t)total_iters),
+                              cudaMemcpyDeviceToHost, h->stream),
+           "[CameraTracker::TrackFrame] read-back failed");
+  DFK_CUDA(h, cudaMemcpyAsync(host_sys, h->out_dev, sizeof(float) * 29, cudaMemcpyDeviceToHost, h->stream),
+           "[CameraTracker::TrackFrame] read-back failed");
+  DFK_CUDA(h, cudaStreamSynchronize(h->stream), "[CameraTracker::TrackFrame] stream synchronize failed");
+  memcpy(pose_ck, h->track_host, sizeof(float) * 7);
+  uint32_t inl = 0;
+  memcpy(&inl, &host_sys[28], 4);
+  // camera_tracker.cpp:65-69: statistics of the last evaluated system (the reference records them at level 0)
+  if (inlier_fraction) *inlier_fraction = last_area ? (float)inl / (float)last_area : 0.0f;
+  if (error) *error = inl != 0 ? host_sys[27] / (float)inl : INFINITY;
+  if (last_system) memcpy(last_system, host_sys, sizeof(float) * 29);
+  if (history) memcpy(history, h->track_host + 8, sizeof(float) * 36 * (size_t)total_iters);
   return DFK_OK;
 }
 

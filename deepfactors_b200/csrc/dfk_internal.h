@@ -118,7 +118,9 @@ struct View {
 };
 cudaError_t launch_se3_step(const PixelCam& pc, float huber_delta, int width, int height, View img0, View img1,
                             View dpt0, View grad1, bool grad_aligned, float* scratch, unsigned int* counter,
-                            float* out_dev /*29 floats: 21 JtJ, 6 Jtr, res, inliers bits*/, cudaStream_t s);
+                            float* out_dev /*29 floats: 21 JtJ, 6 Jtr, res, inliers bits*/, cudaStream_t s,
+                            float* pose_dev = nullptr /*tracking mode: pose read from / updated in device memory*/,
+                            float* history_dev = nullptr /*36 floats: the 29 above + the pose they were evaluated at*/);
 cudaError_t launch_eval_error(const PixelCam& pc, float huber_delta, int width, int height, View img0, View img1,
                               View dpt0, float* scratch, unsigned int* counter, float* out_dev /*2*/, cudaStream_t s);
 cudaError_t launch_warp(const PixelCam& pc, int width, int height, View img0, View img1, View dpt0, float* img2,

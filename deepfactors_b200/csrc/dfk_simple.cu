@@ -29,7 +29,7 @@ constexpr int kWarps = kThreads / 32;
 // Block-level reduction of NV floats + one counter, then last-block finalize.
 // out[0..NV) = sums, out[NV] = counter bits.  scratch: gridDim.x * 32 floats.  NV <= 31.
 template <int NV>
-__device__ __forceinline__ void reduce_finalize(float (&v)[NV], unsigned int cnt, float* __restrict__ scratch,
+__device__ __forceinline__ bool reduce_finalize(float (&v)[NV], unsigned int cnt, float* __restrict__ scratch,
                                                 unsigned int* __restrict__ counter, float* __restrict__ out)
 {
   static_assert(NV <= 31, "one scratch row is 32 floats");
@@ -66,7 +66,7 @@ __device__ __forceinline__ void reduce_finalize(float (&v)[NV], unsigned int cnt
     is_last = (ticket == gridDim.x - 1);
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return false;
   __threadfence();
   // last block: warp w sums blocks w, w+kWarps, ... ; then warp order
   float s = 0.0f;
@@ -95,14 +95,85 @@ __device__ __forceinline__ void reduce_finalize(float (&v)[NV], unsigned int cnt
     }
   }
   if (threadIdx.x == 0) *counter = 0;  // self-resetting for the next launch on this stream
+  return true;
+}
+
+// ------------------------------------------------------------------------------ on-device Gauss-Newton update
+// camera_tracker.cpp:59-63: update = -JtJ.ldlt().solve(Jtr); translation += update.head<3>();
+// so3 = SO3::exp(update.tail<3>()) * so3.  6x6 LDL^T without pivoting (the matrix is a sum of outer products);
+// returns false (pose untouched) when a pivot is not positive, e.g. zero inliers.
+__device__ inline bool gn_update_pose(const float* __restrict__ sys /*21 JtJ packed upper, 6 Jtr*/, float* pose /*qx qy qz qw tx ty tz*/)
+{
+  float A[6][6], b[6];
+  int h = 0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = r; c < 6; ++c) {
+      A[r][c] = sys[h];
+      A[c][r] = sys[h];
+      ++h;
+    }
+  for (int r = 0; r < 6; ++r) b[r] = -sys[21 + r];
+  float L[6][6], D[6];
+  for (int j = 0; j < 6; ++j) {
+    float d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+    if (!(d > 0.0f)) return false;
+    D[j] = d;
+    for (int i = j + 1; i < 6; ++i) {
+      float v = A[i][j];
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * D[k];
+      L[i][j] = v / d;
+    }
+  }
+  float x[6];
+  for (int i = 0; i < 6; ++i) {  // L y = b
+    float v = b[i];
+    for (int k = 0; k < i; ++k) v -= L[i][k] * x[k];
+    x[i] = v;
+  }
+  for (int i = 0; i < 6; ++i) x[i] /= D[i];
+  for (int i = 5; i >= 0; --i) {  // L^T x = y
+    float v = x[i];
+    for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k];
+    x[i] = v;
+  }
+  // Sophus SO3::exp (quaternion form) and left multiplication, then renormalisation
+  const float th2 = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
+  const float th = sqrtf(th2);
+  float im, re;
+  if (th < 1e-10f) {
+    im = 0.5f - th2 * (1.0f / 48.0f) + th2 * th2 * (1.0f / 3840.0f);
+    re = 1.0f - 0.5f * th2 + th2 * th2 * (1.0f / 384.0f);
+  } else {
+    im = sinf(0.5f * th) / th;
+    re = cosf(0.5f * th);
+  }
+  const float ax = im * x[3], ay = im * x[4], az = im * x[5], aw = re;
+  const float bx = pose[0], by = pose[1], bz = pose[2], bw = pose[3];
+  float qx = aw * bx + ax * bw + ay * bz - az * by;
+  float qy = aw * by - ax * bz + ay * bw + az * bx;
+  float qz = aw * bz + ax * by - ay * bx + az * bw;
+  float qw = aw * bw - ax * bx - ay * by - az * bz;
+  const float n = sqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
+  pose[0] = qx / n; pose[1] = qy / n; pose[2] = qz / n; pose[3] = qw / n;
+  pose[4] += x[0]; pose[5] += x[1]; pose[6] += x[2];
+  return true;
 }
 
 // ------------------------------------------------------------------------------ SE3 RunStep
 __global__ void __launch_bounds__(kThreads)
 se3_step_kernel(PixelCam pc, float huber_delta, int width, int height, View img0, View img1, View dpt0, View grad1,
                 bool grad_aligned, float* __restrict__ scratch, unsigned int* __restrict__ counter,
-                float* __restrict__ out)
+                float* __restrict__ out, float* pose_dev, float* __restrict__ history)
 {
+  // tracking mode (pose_dev != nullptr): the pose lives in device memory; the last block of the previous launch
+  // updated it, this launch reads it, and its own last block applies the next Gauss-Newton update.
+  if (pose_dev) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pc.q[k] = pose_dev[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pc.t[k] = pose_dev[4 + k];
+  }
   float acc[28];  // 21 JtJ (packed upper), 6 Jtr, 1 residual
 #pragma unroll
   for (int i = 0; i < 28; ++i) acc[i] = 0.0f;
@@ -139,7 +210,28 @@ se3_step_kernel(PixelCam pc, float huber_delta, int width, int height, View img0
       }
     }
   }
-  reduce_finalize<28>(acc, inl, scratch, counter, out);
+  const bool last = reduce_finalize<28>(acc, inl, scratch, counter, out);
+  if (pose_dev && last) {
+    __syncthreads();  // out[0..28] was written by warp 0 of this block
+    if (threadIdx.x == 0) {
+      float pose[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) pose[k] = pose_dev[k];
+      if (history) {  // [29 system | 7 pose the system was evaluated at]
+#pragma unroll 1
+        for (int k = 0; k < 29; ++k) history[k] = out[k];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) history[29 + k] = pose[k];
+      }
+      float sys[27];
+#pragma unroll 1
+      for (int k = 0; k < 27; ++k) sys[k] = out[k];
+      if (gn_update_pose(sys, pose)) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) pose_dev[k] = pose[k];
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------ EvaluateError
@@ -334,10 +426,11 @@ inline int grid_for(int area)
 
 cudaError_t launch_se3_step(const PixelCam& pc, float huber_delta, int width, int height, View img0, View img1,
                             View dpt0, View grad1, bool grad_aligned, float* scratch, unsigned int* counter,
-                            float* out_dev, cudaStream_t s)
+                            float* out_dev, cudaStream_t s, float* pose_dev, float* history_dev)
 {
   se3_step_kernel<<<grid_for(width * height), kThreads, 0, s>>>(pc, huber_delta, width, height, img0, img1, dpt0,
-                                                                grad1, grad_aligned, scratch, counter, out_dev);
+                                                                grad1, grad_aligned, scratch, counter, out_dev,
+                                                                pose_dev, history_dev);
   return cudaGetLastError();
 }
 

@@ -32,6 +32,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../dfk.h"
@@ -327,6 +328,33 @@ public:
   {
     huber_delta_ = val;
     detail::Check(h_.get(), dfk_se3_set_huber_delta(h_.get(), val));
+  }
+
+  // The loop of CameraTracker::TrackFrame (core/system/camera_tracker.cpp:48-70) as ONE call: for level =
+  // levels-1 .. 0, iterations_per_level[level] times { RunStep; update = -JtJ.ldlt().solve(Jtr); t += update.head<3>();
+  // so3 = exp(update.tail<3>()) * so3 } with the solve and the retraction done on the device and a single read-back.
+  // The pyramids are anything indexable by level (vc::RuntimeBufferPyramidManaged::operator[], std::vector of
+  // views, SyncedBufferPyramid::GetGpuLevel results collected in a vector); camera_pyr[level] is the level's camera.
+  // pose_ck is updated in place; returns {inliers / area, residual / inliers} of the last evaluated system, the two
+  // numbers TrackFrame stores in inliers_ / error_ (:65-69).
+  template <typename SE3T, typename CamPyr, typename ImagePyr0, typename ImagePyr1, typename DepthPyr, typename GradPyr>
+  std::pair<float, float> TrackLevels(SE3T& pose_ck, const CamPyr& camera_pyr, const ImagePyr0& pyr_img0,
+                                      const ImagePyr1& pyr_img1, const DepthPyr& pyr_dpt0, const GradPyr& pyr_grad1,
+                                      const std::vector<int>& iterations_per_level)
+  {
+    std::vector<DfkTrackLevel> lv(iterations_per_level.size());
+    for (std::size_t l = 0; l < lv.size(); ++l) {
+      lv[l].cam = detail::Cam(camera_pyr[l]);
+      lv[l].img0 = detail::View(pyr_img0[l], 1);
+      lv[l].img1 = detail::View(pyr_img1[l], 1);
+      lv[l].dpt0 = detail::View(pyr_dpt0[l], 1);
+      lv[l].grad1 = detail::View(pyr_grad1[l], 2);
+      lv[l].iterations = iterations_per_level[l];
+    }
+    float frac = 0.f, err = 0.f;
+    detail::Check(h_.get(), dfk_se3_track(h_.get(), pose_ck.data(), lv.data(), static_cast<int>(lv.size()), &frac, &err,
+                                          nullptr, nullptr, 0));
+    return std::make_pair(frac, err);
   }
 
 private:

@@ -186,6 +186,32 @@ DfkStatus dfk_se3_run_step(DfkHandle h, const float se3[7], const DfkCamera* cam
                            const DfkImage* grad1,
                            float* JtJ, float* Jtr, float* residual, uint64_t* inliers);
 
+/* One pyramid level of a tracking problem: keyframe image/depth (img0, dpt0), live frame image/gradient (img1,
+ * grad1), the level's camera and the Gauss-Newton iteration count (TrackerConfig::iterations_per_level,
+ * core/system/camera_tracker.h:45-50). */
+typedef struct DfkTrackLevel {
+  DfkCamera cam;
+  DfkImage img0, img1, dpt0, grad1;
+  int iterations;
+} DfkTrackLevel;
+
+/* CameraTracker::TrackFrame (core/system/camera_tracker.cpp:42-69): coarse-to-fine Gauss-Newton on pose_ck.
+ * levels[0] is the finest level; iteration runs from levels[num_levels-1] down to levels[0].  Per iteration the
+ * reference does SE3Aligner::RunStep + cudaDeviceSynchronize + a 120-byte D2H + a host 6x6 LDLT + retraction
+ * (update = -JtJ.ldlt().solve(Jtr); t += update.head<3>(); so3 = exp(update.tail<3>()) * so3); here every iteration
+ * is ONE launch whose last block solves the 6x6 system and retracts the pose in device memory, all iterations are
+ * enqueued back to back and there is a single read-back at the end.
+ *   pose_ck         in/out, (qx,qy,qz,qw,tx,ty,tz)
+ *   inlier_fraction inliers / area and error = residual / inliers of the last evaluated system (the reference
+ *   error           records them on the last iteration of level 0, :65-69); error = +inf when inliers == 0
+ *   last_system     optional, 29 floats [JtJ packed upper 21 | Jtr 6 | residual | inliers (u32 bits)]
+ *   history         optional, history_capacity x 36 floats: per iteration the 29 floats above + the pose (7) they
+ *                   were evaluated at
+ * An iteration whose system is not positive definite (e.g. zero inliers) leaves the pose untouched. */
+DfkStatus dfk_se3_track(DfkHandle h, float pose_ck[7], const DfkTrackLevel* levels, int num_levels,
+                        float* inlier_fraction, float* error, float* last_system, float* history,
+                        int history_capacity);
+
 /* SE3Aligner<float>::Warp (cu_se3aligner.h:58-63, cu_se3aligner.cpp:125-151): renders img1
  * into frame 0 (img2, 0 where invalid); residual = SIGNED sum(img0 - sampled) (:106). */
 DfkStatus dfk_se3_warp(DfkHandle h, const float se3[7], const DfkCamera* cam,

@@ -241,6 +241,36 @@ def se3_warp(se3, cam, img0, img1, dpt0, *, precision="f32"):
     return img2, float(res.value), int(inl.value)
 
 
+def se3_track(pose_ck, cams, pyr_img0, pyr_img1, pyr_dpt0, pyr_grad1, iterations_per_level, huber_delta=0.1, *,
+              precision="f64"):
+    """CameraTracker::TrackFrame (core/system/camera_tracker.cpp:42-69): levels coarse -> fine, per iteration
+    SE3Aligner::RunStep, update = -JtJ.ldlt().solve(Jtr), t += update[:3], so3 = exp(update[3:]) * so3.
+    Returns (pose, inlier_fraction, error, history) with history[i] = (StepResult, pose it was evaluated at)."""
+    pose = np.asarray(pose_ck, dtype=np.float64).copy()
+    hist = []
+    frac, err = 0.0, float("inf")
+    for level in range(len(cams) - 1, -1, -1):
+        for _ in range(int(iterations_per_level[level])):
+            r = se3_run_step(pose.astype(np.float32), cams[level], pyr_img0[level], pyr_img1[level], pyr_dpt0[level],
+                             pyr_grad1[level], huber_delta, precision=precision)
+            hist.append((r, pose.copy()))
+            frac = r.inliers / float(pyr_img1[level].shape[0] * pyr_img1[level].shape[1])
+            err = r.residual / r.inliers if r.inliers else float("inf")
+            if r.inliers == 0:
+                continue
+            Hd = np.zeros((6, 6))
+            Hd[np.triu_indices(6)] = np.asarray(r.JtJ, dtype=np.float64)
+            Hd = Hd + np.triu(Hd, 1).T
+            upd = -np.linalg.solve(Hd, np.asarray(r.Jtr, dtype=np.float64))
+            dq = so3_exp(upd[3:6])
+            x1, y1, z1, w1 = dq
+            x2, y2, z2, w2 = pose[:4]
+            q = np.array([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                          w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2])
+            pose = np.concatenate([q / np.linalg.norm(q), pose[4:7] + upd[:3]])
+    return pose, frac, err, hist
+
+
 def update_depth(code, prx_orig, prx_jac, avg_dpt=2.0):
     code = np.ascontiguousarray(code, dtype=np.float32)
     prx_orig, prx_jac = _f32(prx_orig), _f32(prx_jac)

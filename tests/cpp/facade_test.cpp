@@ -108,6 +108,21 @@ int main()
                       &res6f, &inl6f);
   EXPECT(r6.inliers == inl6f);
 
+  // CameraTracker::TrackFrame's loop as one device-side call: a single level, 8 Gauss-Newton iterations starting at
+  // pose1 must not increase the mean Huber-weighted residual, and moves the pose
+  {
+    SE3 trk = pose1;
+    std::vector<PinholeCamera> cams(1, cam);
+    std::vector<Image2DView<float>> k0(1, i0), f1(1, i1), kd(1, dp);
+    std::vector<Image2DView<Grad>> g1(1, gr);
+    const auto stats = se3.TrackLevels(trk, cams, k0, f1, kd, g1, std::vector<int>(1, 8));
+    EXPECT(stats.first > 0.3f && stats.first <= 1.0f);
+    EXPECT(stats.second <= r6.residual / (float)r6.inliers * 1.0001f);
+    float moved = 0.f;
+    for (int k = 0; k < 7; ++k) moved += std::fabs(trk.data()[k] - pose1.data()[k]);
+    EXPECT(moved > 1e-4f);
+  }
+
   bool threw = false;
   try {
     aligner.SetStepThreadsBlocks(33, 11);  // CHECK_EQ(threads % 32, 0) in the reference

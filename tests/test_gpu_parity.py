@@ -232,6 +232,68 @@ def test_se3_image_alignment_converges_on_gpu(torch_mod, oracle, golden):
     assert err <= 1e-3
 
 
+def test_camera_tracker_device_loop_matches_host_loop(torch_mod, oracle, golden):
+    """CameraTracker::TrackFrame (camera_tracker.cpp:42-69) with the whole coarse-to-fine loop on the device:
+    every iteration's system == the oracle's at the same pose, every on-device LDLT + retraction == numpy's,
+    the final pose / inlier fraction / error == the oracle's host loop."""
+    torch = torch_mod
+    from deepfactors_b200.aligners import CameraTracker, TrackerConfig
+    from helpers import tracking_pyramid
+    cams, p0, p1, pd, pg = tracking_pyramid(golden, oracle, 3)
+    iters = (10, 5, 4)
+    cfg = TrackerConfig(pyramid_levels=3, iterations_per_level=iters, huber_delta=0.1)
+    trk = CameraTracker(cams, cfg)
+    up = lambda lst, extra=0: [pitched(torch, a, extra) for a in lst]
+    trk.SetKeyframe(up(p0), up(pd, 3))
+    pose = trk.TrackFrame(up(p1, 5), up(pg), keep_history=True)
+    o_pose, o_frac, o_err, o_hist = oracle.se3_track(se3.identity(np.float64), cams, p0, p1, pd, pg, iters, 0.1)
+    hist = trk.history_
+    assert hist.shape == (sum(iters), 36) and len(o_hist) == sum(iters)
+    # first iteration: same pose (identity) -> the strict single-step bar
+    g0 = hist[0]
+    assert int(g0[28:29].view(np.uint32)[0]) == oracle.se3_run_step(se3.identity(), cams[2], p0[2], p1[2], pd[2], pg[2],
+                                                                   0.1).inliers
+    assert np.abs(g0[:21] - o_hist[0][0].JtJ).max() <= 2e-5 * np.abs(o_hist[0][0].JtJ).max()
+    # every iteration: the pose of iteration k+1 is numpy's solve + retraction applied to the device's own system k
+    level_of = [l for l in (2, 1, 0) for _ in range(iters[l])]
+    for k in range(len(hist) - 1):
+        Hk = np.zeros((6, 6))
+        Hk[np.triu_indices(6)] = hist[k][:21].astype(np.float64)
+        Hk = Hk + np.triu(Hk, 1).T
+        want = se3.se3_solve_and_update(Hk, hist[k][21:27].astype(np.float64), hist[k][29:36].astype(np.float64))
+        assert np.abs(want - hist[k + 1][29:36]).max() <= 5e-6, f"on-device update of iteration {k}"
+        # and the device's system at its pose == the oracle's at that same pose
+        r = oracle.se3_run_step(hist[k][29:36], cams[level_of[k]], p0[level_of[k]], p1[level_of[k]], pd[level_of[k]],
+                                pg[level_of[k]], 0.1, precision="f64")
+        assert np.abs(hist[k][:21] - r.JtJ).max() <= 2e-5 * np.abs(r.JtJ).max(), f"system of iteration {k}"
+    # end result vs the oracle's own loop (fp64 steps, numpy solve)
+    assert np.abs(pose - o_pose).max() <= 1e-4, (pose, o_pose)
+    assert abs(trk.GetInliers() - o_frac) <= 2e-3
+    assert abs(trk.GetError() - o_err) <= 1e-3 * o_err
+    # a second frame continues from the tracked pose (camera_tracker.cpp keeps pose_ck_ across frames)
+    before = trk.GetError()
+    trk.TrackFrame(up(p1), up(pg))
+    assert trk.GetError() <= before * 1.0001
+
+
+def test_camera_tracker_converges_and_handles_no_overlap(torch_mod, oracle, golden):
+    """tests/ut_se3aligner.cpp:173-211 as one device-side loop: 40 GN iterations at level 0, error <= 1e-3; and a pose
+    with zero overlap leaves the estimate untouched with error = +inf (camera_tracker.cpp:68)"""
+    torch = torch_mod
+    from deepfactors_b200.aligners import CameraTracker, TrackerConfig
+    from helpers import tracking_pyramid
+    cams, p0, p1, pd, pg = tracking_pyramid(golden, oracle, 1)
+    trk = CameraTracker(cams, TrackerConfig(pyramid_levels=1, iterations_per_level=(40,), huber_delta=0.1))
+    up = lambda lst: [pitched(torch, a) for a in lst]
+    trk.SetKeyframe(up(p0), up(pd))
+    trk.TrackFrame(up(p1), up(pg))
+    assert trk.GetError() <= 1e-3 and trk.GetInliers() > 0.5
+    far = se3.make_pose([0, 0, 0], [0, 0, 100.0])
+    trk.pose_ck_ = far.copy()
+    out = trk.TrackFrame(up(p1), up(pg))
+    assert np.array_equal(out, far) and trk.GetError() == float("inf") and trk.GetInliers() == 0.0
+
+
 def test_image_proc_matches_oracle_and_opencv(torch_mod, oracle, golden):
     torch = torch_mod
     from deepfactors_b200.aligners import GaussianBlurDown, SobelGradients, SquaredError, UpdateDepth

@@ -365,3 +365,18 @@ def test_update_depth_and_squared_error(oracle):
     ref = float(((a.astype(np.float64) - b) ** 2).sum())
     assert abs(oracle.squared_error(a, b) - ref) < 1e-4 * ref
     assert abs(oracle.squared_error(a, b, "f64") - ref) < 1e-9 * ref
+
+
+def test_tracker_loop_converges_coarse_to_fine(oracle, golden):
+    """CameraTracker::TrackFrame restated (camera_tracker.cpp:42-69) on the reference's own test pair: the 3-level
+    10/5/4 schedule of the default TrackerConfig reaches the same minimum as 40 single-level iterations
+    (ut_se3aligner.cpp:173-211 bar: mean residual <= 1e-3)"""
+    from helpers import tracking_pyramid
+    cams, p0, p1, pd, pg = tracking_pyramid(golden, oracle, 3)
+    pose3, frac3, err3, hist = oracle.se3_track(se3.identity(np.float64), cams, p0, p1, pd, pg, (10, 5, 4), 0.1)
+    pose1, frac1, err1, _ = oracle.se3_track(se3.identity(np.float64), cams[:1], p0[:1], p1[:1], pd[:1], pg[:1], (40,), 0.1)
+    assert len(hist) == 19 and err3 <= 1e-3 and err1 <= 1e-3
+    assert np.abs(pose3 - pose1).max() <= 1e-4 and abs(frac3 - frac1) <= 1e-3
+    # the coarse levels do the work: the error at the first fine-level iteration is already close to the final one
+    first_fine = hist[15][0]
+    assert first_fine.residual / first_fine.inliers <= 2.0 * err3

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdfk.so")
+# DFK_LIB: another build of the same library (A/B measurements of kernel variants); default = the in-tree build
+LIB_PATH = os.environ.get("DFK_LIB") or os.path.join(_HERE, "libdfk.so")
 
 DFK_OK = 0
 DFK_ERR_INVALID_ARG = 1

@@ -375,7 +375,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         // tensor core).  Rotated float4 order keeps reads (row = slot) and writes (row = rank) free of bank
         // conflicts; all rows are read into registers before any is overwritten (same warp => __syncwarp).
         float4 rowv[C / 4];
+#ifdef DFK_EXP_NOCOMPACT
+        if (false) {
+#else
         if (ok) {
+#endif
           // rows are 128-byte aligned: chunk (k4 ^ (lane & 7)) of row s  ==  (row address + (lane & 7) * 16) ^ (k4 * 16)
           const uint32_t src = smem_u32(&sm.jc[st][s * C]) + ((uint32_t)(lane & 7) << 4);
 #pragma unroll
@@ -396,6 +400,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           const int c = blk0 + rank;
           const float sc = feat[0];
           const uint32_t dst = smem_u32(&sm.jc[st][c * C]) + ((uint32_t)(lane & 7) << 4);
+#ifndef DFK_EXP_NOCOMPACT
 #pragma unroll
           for (int k4 = 0; k4 < C / 4; ++k4) {
             const float4 v = rowv[k4];
@@ -403,6 +408,9 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
                          "f"(sc * v.y), "f"(sc * v.z), "f"(sc * v.w)
                          : "memory");
           }
+#else
+          (void)sc; (void)dst;
+#endif
 #pragma unroll
           for (int f = 1; f < 8; ++f) sm.feat[fb][f][c] = feat[f];
         }
@@ -470,7 +478,9 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
               const int nk = (meta.nv[2 * h + bb] + 7) >> 3;
               for (int ks = 0; ks < nk; ++ks) {
                 const int kc = 4 * bb + ks;  // 8-pixel k-step inside the half
+#ifndef DFK_EXP_NOMMA
                 umma_tf32_ts(d_addr, tbase + A_COL + HALF * h + 8 * kc, bdesc0 + (uint64_t)((kc * 256) >> 4), idesc, !first);
+#endif
                 first = false;
               }
             }
@@ -523,7 +533,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         // three passes of 16 accumulator columns keep the register footprint small.  The first chain of an
         // item in this CTA stores, later chains add with fire-and-forget red.global.add.f32: this thread is the
         // only writer of its row and issues its updates in program order, so the sum order is fixed.
+#ifdef DFK_EXP_NODRAIN
+        if (false) {
+#else
         if (valid > 0 || fresh) {
+#endif
 #pragma unroll 1
           for (int pass = 0; pass < 3; ++pass) {
             const int nq = pass < 2 ? 4 : (kTcCols - 32) / 4;  // float4 per pass (columns 40..47 are padding)
@@ -615,7 +629,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           unsigned char* bh = sm.B[h];
           // each half = two 32-pixel blocks; operand group g builds block g of the half: 32 row loads, one
           // 32-column tcgen05.st (registers -> TMEM lanes), and for the h rows the K-major B tile
+#ifdef DFK_EXP_NOOPBUILD
+          if (false) {
+#else
           if (nv > 0) {
+#endif
             const int c0 = HALF * h + 32 * ogrp;  // first compacted pixel of the block
             const uint32_t a_taddr = lane_taddr + A_COL + c0;
             uint32_t v[32];

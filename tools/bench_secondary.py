@@ -121,6 +121,34 @@ def main():
     timed("SobelGradients", lambda: SobelGradients(d["img1"], grad_out), px * 12)
     timed("GaussianBlurDown", lambda: GaussianBlurDown(d["img1"], half), px * 5)
 
+    # ---- CameraTracker::TrackFrame: 3 levels x (10, 5, 4) iterations (data/flags defaults: 19 SE3 steps per frame) --------
+    from deepfactors_b200 import se3
+    from deepfactors_b200.aligners import CameraTracker, TrackerConfig
+    tp = synth.make_pair(640, 480, 8, 3, seed=9)
+    lv = [upload(L) for L in tp.levels]
+    cams = [L.cam for L in tp.levels]
+    iters = (10, 5, 4)
+    trk = CameraTracker(cams, TrackerConfig(pyramid_levels=3, iterations_per_level=iters, huber_delta=0.1))
+    trk.SetKeyframe([x["img0"] for x in lv], [x["dpt0"] for x in lv])
+    img1s, grads = [x["img1"] for x in lv], [x["grad1"] for x in lv]
+
+    def device_loop():
+        trk.Reset()
+        trk.TrackFrame(img1s, grads)
+
+    def host_loop():  # what the reference does: synchronous step, host solve, next step (camera_tracker.cpp:48-63)
+        pose = se3.identity(np.float64)
+        for level in (2, 1, 0):
+            for _ in range(iters[level]):
+                r = se.RunStep(pose.astype(np.float32), cams[level], lv[level]["img0"], lv[level]["img1"], lv[level]["dpt0"],
+                               lv[level]["grad1"])
+                pose = se3.se3_solve_and_update(r.toDenseMatrix(), r.Jtr, pose)
+        return pose
+
+    bytes_track = sum(iters[l] * (640 >> l) * (480 >> l) * 20 for l in range(3))
+    timed("CameraTracker::TrackFrame 19 iterations, device-side loop (dfk_se3_track)", device_loop, bytes_track)
+    timed("CameraTracker::TrackFrame 19 iterations, per-step API + host solve (reference structure)", host_loop, bytes_track)
+
 
 if __name__ == "__main__":
     main()

@@ -45,6 +45,7 @@ namespace {
 
 constexpr int C = 32;
 constexpr int TILE = kTcTilePixels;  // 128
+constexpr int FEAT_STRIDE = TILE + 4;  // floats per feature row in shared memory (see Smem::feat)
 constexpr int HALF = 64;
 constexpr int STAGES = 4;
 constexpr int FE_GROUPS = 2;         // front-end group g handles the CTA's tiles i with i % 2 == g
@@ -91,7 +92,9 @@ struct Smem {
   alignas(128) unsigned char B[2][B_HALF_BYTES];
   alignas(16) float img0[STAGES][TILE];
   alignas(16) float dpt0[STAGES][TILE];
-  alignas(16) float feat[2][8][TILE];  // K-major per-pixel scalars of the compacted pixels: s, wa0..5, wr
+  // K-major per-pixel scalars of the compacted pixels: s, wa0..5, wr.  Rows are padded by one float4 so that the pose
+  // operand warp, whose lanes read the SAME pixel chunk of 7 different rows, hits 7 different bank groups
+  alignas(16) float feat[2][8][FEAT_STRIDE];
   alignas(16) int sid[2][TILE];        // slot (row of the jc stage) of each compacted pixel
   alignas(8) uint64_t tma_full[STAGES];
   uint64_t stage_empty[STAGES];  // the operand warps are done with the ring stage
@@ -620,7 +623,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         const float4* __restrict__ featp = reinterpret_cast<const float4*>(sm.feat[fb]);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          const int nv = meta.nv[2 * h + ogrp];  // this group's block of the half
+          const int nv = sm.meta[fb].nv[2 * h + ogrp];  // this group's block of the half (shared memory: no local-array indexing)
           // A/B half h was last read by the MMAs of tile i-1
           tm.start();
           mbar_wait(&sm.a_empty[h], (i & 1u) ^ 1u);
@@ -658,7 +661,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
             } else {
               // pose / residual features: lanes 0-6 = h of feature 1+lane, lanes 7-13 = l of feature 1+(lane-7)
               const int f = 1 + (lane < 7 ? lane : (lane < 14 ? lane - 7 : 0));
-              const float4* fp = featp + f * (TILE / 4) + (c0 >> 2);
+              const float4* fp = featp + f * (FEAT_STRIDE / 4) + (c0 >> 2);
               float4 x[8];
 #pragma unroll
               for (int q = 0; q < 8; ++q) x[q] = fp[q];
@@ -683,7 +686,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           }
           tm.lap(t_build);
           tmem_wait_st();
-          fence_proxy_async_smem();
+          if (ow != 1) fence_proxy_async_smem();  // the code-l warp wrote TMEM only, no B rows
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.a_full[h]);

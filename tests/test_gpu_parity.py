@@ -291,7 +291,7 @@ def test_camera_tracker_converges_and_handles_no_overlap(torch_mod, oracle, gold
     trk.SetKeyframe(up(p0), up(pd))
     trk.TrackFrame(up(p1), up(pg))
     assert trk.GetError() <= 1e-3 and trk.GetInliers() > 0.5
-    far = se3.make_pose([0, 0, 0], [0, 0, 100.0])
+    far = se3.make_pose([0, 0, 0], [0, 0, -100.0])  # every keyframe point lands behind the live camera
     trk.pose_ck_ = far.copy()
     out = trk.TrackFrame(up(p1), up(pg))
     assert np.array_equal(out, far) and trk.GetError() == float("inf") and trk.GetInliers() == 0.0

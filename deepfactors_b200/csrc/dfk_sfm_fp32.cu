@@ -187,7 +187,7 @@ sfm_step_fp32_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&sm.full_tma[s], 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sm.m_full[b], kFeThreads);
+      mbar_init(&sm.m_full[b], kFeWarps);  // one arrival per front-end warp (every arrival wakes the waiters)
       mbar_init(&sm.m_empty[b], NBLK);
     }
     mbar_fence_init();
@@ -334,7 +334,8 @@ sfm_step_fp32_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
         sm.meta[buf].item_changed = changed ? 1 : 0;
         sm.meta[buf].slot = (int)I.slot;
       }
-      mbar_arrive(&sm.m_full[buf]);     // release: M tile + meta visible to the Gram warps
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.m_full[buf]);  // release: M tile + meta visible to the Gram warps
       named_bar_sync(1, kFeThreads);    // all front-end threads are done with ring stage `st`
       if (tid == 0) {
         const int gn = g + kStages;

@@ -240,7 +240,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       mbar_init(&sm.stage_empty[s], 6);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sm.feat_full[b], FE_THREADS);
+      mbar_init(&sm.feat_full[b], FE_THREADS / 32);  // one arrival per front-end warp: every arrival wakes the waiters
       mbar_init(&sm.feat_empty[b], 7);  // 2 x 3 operand warps + the control thread (it reads meta[b])
       mbar_init(&sm.a_full[b], 6);
       mbar_init(&sm.a_empty[b], 1);
@@ -431,7 +431,8 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           sm.meta[fb].item_changed = seq_changed ? 1 : 0;
           sm.meta[fb].slot = (int)I.slot;
         }
-        mbar_arrive(&sm.feat_full[fb]);
+        __syncwarp();  // the warp's rows / feat entries / meta are ordered before lane 0's release
+        if (lane == 0) mbar_arrive(&sm.feat_full[fb]);
         tm.lap(t_fe_write);
       }
       if (tm.on) {

@@ -174,7 +174,7 @@ sfm_step_wide_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&sm.full_tma[s], 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sm.m_full[b], FE);
+      mbar_init(&sm.m_full[b], W::FE_WARPS);  // one arrival per front-end warp (every arrival wakes the waiters)
       mbar_init(&sm.m_empty[b], W::GRAM_WARPS);
     }
     mbar_fence_init();
@@ -285,7 +285,8 @@ sfm_step_wide_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
         sm.meta[buf].item_changed = changed ? 1 : 0;
         sm.meta[buf].slot = (int)I.slot;
       }
-      mbar_arrive(&sm.m_full[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.m_full[buf]);
       named_bar_sync(1, FE);  // all front-end threads are done with ring stage `st`
       if (tid == 0) {
         const int gn = g + kStages;

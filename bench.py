@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--code-sigma", type=float, default=0.0,
                     help="std of the latent code used to decode dpt0 (0 = the reference test's zero code, smooth depth; "
                          ">0 adds per-pixel depth noise through the iid synthetic code Jacobian)")
+    ap.add_argument("--fused-depth", action="store_true",
+                    help="decode dpt0 from prx_orig + code inside the launch (UpdateDepth + RunStep in one pass; "
+                         "28+4C algorithmic bytes per pixel instead of 24+4C, and no separate UpdateDepth pass)")
     ap.add_argument("--identity-pose", action="store_true", help="100%% inliers (worst-case work) instead of the ~60%% of the reference test poses")
     return ap.parse_args()
 
@@ -228,6 +231,8 @@ def main():
     host_levels = []
     for L in base.levels:
         host_levels.append(dict(img0=L.img0, img1=L.img1, dpt0=L.dpt0, prx0_jac=L.prx_jac, grad1=L.grad1))
+        if args.fused_depth:
+            host_levels[-1]["prx_orig"] = L.prx_orig
     pairs_dev = []
     for p in range(P):
         lv = []
@@ -247,6 +252,8 @@ def main():
         for d in lv:
             items.append(dict(pose0=base.pose0, pose1=base.pose1, cam=d["cam"], img0=d["img0"], img1=d["img1"],
                               dpt0=d["dpt0"], valid0=d["valid0"], prx0_jac=d["prx0_jac"], grad1=d["grad1"]))
+            if args.fused_depth:
+                items[-1].update(prx_orig=d["prx_orig"], code=base.code)
     work = al.make_work_items(items)
     rec_floats = _lib.record_floats(CS)
     # window Hessian buffer: every rank owns P*LEVELS rows; all-reduce(sum) assembles the window
@@ -326,7 +333,9 @@ def main():
     d2h = LEVELS * rec_floats * 4
 
     e2e_items = [dict(pose0=base.pose0, pose1=base.pose1, cam=L.cam, img0=sd["img0"], img1=sd["img1"], dpt0=sd["dpt0"],
-                      valid0=sd["valid0"], prx0_jac=sd["prx0_jac"], grad1=sd["grad1"]) for L, sd in zip(base.levels, stage)]
+                      valid0=sd["valid0"], prx0_jac=sd["prx0_jac"], grad1=sd["grad1"],
+                      **(dict(prx_orig=sd["prx_orig"], code=base.code) if args.fused_depth else {}))
+                 for L, sd in zip(base.levels, stage)]
     e2e_work = al.make_work_items(e2e_items)
     e2e_rec_dev = torch.empty((LEVELS, rec_floats), dtype=torch.float32, device=dev)
     e2e_rec_host = torch.empty((LEVELS, rec_floats), dtype=torch.float32).pin_memory()
@@ -362,14 +371,15 @@ def main():
             peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        bytes_per_launch = P * BYTES_PER_EVAL
+        bytes_per_eval = PIXELS * (BYTES_PER_PX + (4 if args.fused_depth else 0))
+        bytes_per_launch = P * bytes_per_eval
         traffic = None  # dram__bytes_read+write of one step-kernel launch, from the committed ncu --set full capture
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and P == 8 and args.gram in ("auto", "tf32x3"):
+        if os.path.exists(tpath) and P == 8 and args.gram in ("auto", "tf32x3") and not args.fused_depth:
             traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = bytes_per_launch / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
-        single["frac_of_hbm_roofline"] = (BYTES_PER_EVAL / (single_ms * 1e-3) / 1e9) / peak
+        single["frac_of_hbm_roofline"] = (bytes_per_eval / (single_ms * 1e-3) / 1e9) / peak
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu, _ = cpu_baseline(args.cpu_seconds, args.code_sigma, args.identity_pose)
@@ -380,7 +390,8 @@ def main():
             "config": {"workload": "single pair 640x480 4-level pyramid, code dim 32 (BASELINE configs[1]); "
                                    f"{P} distinct pairs per step in one persistent launch",
                        "evals_per_step_per_gpu": P, "pixels_per_eval": PIXELS,
-                       "algorithmic_bytes_per_eval": BYTES_PER_EVAL, "gram": args.gram,
+                       "algorithmic_bytes_per_eval": bytes_per_eval, "gram": args.gram,
+                       "fused_depth_decode": bool(args.fused_depth),
                        "poses": "identity (100% inliers)" if args.identity_pose else
                                 "tests/ut_sfmaligner.cpp:254-264 (~60% inliers)",
                        "code_sigma": args.code_sigma,

@@ -52,7 +52,8 @@ class DfkSfmAlignerParams(C.Structure):
 class DfkSfmWorkItem(C.Structure):
     _fields_ = [("pose0", C.c_float * 7), ("pose1", C.c_float * 7), ("cam", DfkCamera),
                 ("img0", DfkImage), ("img1", DfkImage), ("dpt0", DfkImage), ("valid0", DfkImage),
-                ("prx0_jac", DfkImage), ("grad1", DfkImage)]
+                ("prx0_jac", DfkImage), ("grad1", DfkImage),
+                ("prx_orig", DfkImage), ("code", C.POINTER(C.c_float))]  # optional fused depth decode
 
 
 class DfkTrackLevel(C.Structure):

@@ -220,8 +220,11 @@ class SfmAligner:
 
     # ---- batched extension (one persistent launch for many (pair, level) items) -----------------
     def make_work_items(self, items: Sequence[dict]):
-        """items: dicts with pose0, pose1, cam, img0, img1, dpt0, valid0, prx0_jac, grad1."""
+        """items: dicts with pose0, pose1, cam, img0, img1, dpt0, valid0, prx0_jac, grad1; optionally prx_orig + code
+        (fused depth decode: UpdateDepth(code, prx_orig, prx0_jac, avg_dpt, dpt0) happens inside the launch and dpt0
+        becomes an output)."""
         arr = (DfkSfmWorkItem * len(items))()
+        keep = []  # the code arrays must outlive the ctypes pointers
         for k, it in enumerate(items):
             w = arr[k]
             w.pose0 = _pose(it["pose0"])
@@ -229,6 +232,14 @@ class SfmAligner:
             w.cam = _cam(it["cam"])
             w.img0, w.img1, w.dpt0 = _image(it["img0"]), _image(it["img1"]), _image(it["dpt0"])
             w.valid0, w.prx0_jac, w.grad1 = _image(it["valid0"]), _image(it["prx0_jac"], self.CS), _image(it["grad1"], 2)
+            if it.get("code") is not None:
+                code = np.ascontiguousarray(it["code"], dtype=np.float32)
+                if code.shape != (self.CS,):
+                    raise ValueError(f"code must have {self.CS} entries")
+                keep.append(code)
+                w.prx_orig = _image(it["prx_orig"])
+                w.code = code.ctypes.data_as(C.POINTER(C.c_float))
+        arr._keepalive = keep
         return arr
 
     def RunStepBatch(self, work_items, records: torch.Tensor | None = None) -> torch.Tensor:

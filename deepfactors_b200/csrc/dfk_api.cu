@@ -44,6 +44,9 @@ struct DfkContext {
   size_t partials_cap = 0;  // floats
   float* ray_tabs_dev = nullptr;
   size_t ray_tabs_cap = 0;  // floats
+  float* codes_dev = nullptr;  // fused depth decode: code_size floats per work item
+  size_t codes_cap = 0;
+  std::vector<float> codes_host;
   float* records_dev = nullptr;
   size_t records_cap = 0;  // floats
   float* records_host = nullptr;  // pinned
@@ -228,7 +231,7 @@ cudaError_t ensure(T** ptr, size_t* cap, size_t need)
 }
 
 DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, int tile_px, int max_ctas,
-                      float* ray_tabs, SfmLaunchPlan* plan)
+                      float* ray_tabs, const float* codes_dev, SfmLaunchPlan* plan)
 {
   size_t ray_cursor = 0;
   const DfkDenseSfmParams& sp = h->params.sfmparams;
@@ -259,6 +262,21 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
     d.img0_pitch = (uint32_t)(w.img0.pitch_bytes / 4); d.img1_pitch = (uint32_t)(w.img1.pitch_bytes / 4);
     d.dpt0_pitch = (uint32_t)(w.dpt0.pitch_bytes / 4); d.valid0_pitch = (uint32_t)(w.valid0.pitch_bytes / 4);
     d.jac_pitch = (uint32_t)(w.prx0_jac.pitch_bytes / 4); d.grad1_pitch = (uint32_t)(w.grad1.pitch_bytes / 4);
+    d.dpt_out = nullptr; d.dpt_out_pitch = 0; d.code = nullptr;
+    const bool fused = (w.code != nullptr);
+    if (fused) {
+      // UpdateDepth + RunStep in one pass: the tile loader stages prx_orig where it would stage dpt0, the front-end
+      // decodes the depth (bit for bit what dfk_update_depth computes) and writes it to dpt0
+      if (!img_ok(&w.prx_orig, W, H, 1))
+        return fail(h, DFK_ERR_INVALID_ARG,
+                    "[SfmAligner::RunStep] fused depth decode: inconsistent prx_orig view in work item " + std::to_string(i));
+      d.dpt_out = (float*)w.dpt0.ptr;
+      d.dpt_out_pitch = d.dpt0_pitch;
+      d.dpt0 = (const float*)w.prx_orig.ptr;
+      d.dpt0_pitch = (uint32_t)(w.prx_orig.pitch_bytes / 4);
+      d.code = codes_dev + (size_t)i * code_size;
+      memcpy(h->codes_host.data() + (size_t)i * code_size, w.code, sizeof(float) * code_size);
+    }
     d.width = W; d.height = H; d.num_pixels = W * H;
     d.num_tiles = (d.num_pixels + tile_px - 1) / tile_px;
     d.ray_tab = ray_tabs ? ray_tabs + ray_cursor : nullptr;
@@ -274,6 +292,7 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
                       (code_size % 4 == 0);
     if (bulk) d.flags |= ITEM_FLAG_BULK;
     if (aligned(d.grad1, 8) && d.grad1_pitch % 2 == 0) d.flags |= ITEM_FLAG_GRAD_ALIGNED;
+    if (fused) d.flags |= ITEM_FLAG_FUSED_DEPTH;
   }
   const int T = (int)tile_cursor;
   int G = std::min(max_ctas, T);
@@ -368,9 +387,19 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     DFK_CUDA(h, ensure(&h->ray_tabs_dev, &h->ray_tabs_cap, ray_floats), "[SfmAligner::RunStep] scratch allocation failed");
   }
   const int tile_px = tc ? kTcTilePixels : (wide ? sfm_wide_tile_pixels(code_size) : kTilePixels);
+  bool any_fused = false;
+  for (int i = 0; i < n; ++i) any_fused = any_fused || items[i].code != nullptr;
+  if (any_fused) {
+    DFK_CUDA(h, ensure(&h->codes_dev, &h->codes_cap, (size_t)n * code_size), "[SfmAligner::RunStep] scratch allocation failed");
+    h->codes_host.assign((size_t)n * code_size, 0.0f);
+  }
   DfkStatus st = build_items(h, items, n, code_size, tile_px, tc ? 2 * h->num_sms : h->num_sms,
-                             tc ? h->ray_tabs_dev : nullptr, &plan);
+                             tc ? h->ray_tabs_dev : nullptr, h->codes_dev, &plan);
   if (st != DFK_OK) return st;
+  if (any_fused)
+    DFK_CUDA(h, cudaMemcpyAsync(h->codes_dev, h->codes_host.data(), sizeof(float) * (size_t)n * code_size,
+                                cudaMemcpyHostToDevice, h->stream),
+             "[SfmAligner::RunStep] code upload failed");
   const size_t pfloats = tc ? (size_t)kTcPartialFloats : sfm_partial_floats(code_size);
   DFK_CUDA(h, ensure(&h->items_dev, &h->items_cap, (size_t)n), "[SfmAligner::RunStep] scratch allocation failed");
   DFK_CUDA(h, ensure(&h->partials_dev, &h->partials_cap, (size_t)plan.num_partials * pfloats),
@@ -466,6 +495,7 @@ DfkStatus dfk_destroy(DfkHandle h)
   if (h->own_stream) cudaStreamSynchronize(h->own_stream);
   cudaFree(h->simple_scratch); cudaFree(h->counter); cudaFree(h->out_dev); cudaFree(h->code_dev);
   cudaFree(h->track_dev);
+  cudaFree(h->codes_dev);
   if (h->track_host) cudaFreeHost(h->track_host);
   cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev); cudaFree(h->ray_tabs_dev);
   if (h->out_host) cudaFreeHost(h->out_host);
@@ -602,7 +632,7 @@ DfkStatus dfk_sfm_run_step(DfkHandle h, const float pose0[7], const float pose1[
   if (!pose0 || !pose1 || !cam || !img0 || !img1 || !dpt0 || !valid0 || !prx0_jac || !grad1 || !JtJ || !Jtr ||
       !residual || !inliers)
     return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] null argument");
-  DfkSfmWorkItem w;
+  DfkSfmWorkItem w{};  // no fused depth decode: code = NULL
   memcpy(w.pose0, pose0, sizeof(w.pose0));
   memcpy(w.pose1, pose1, sizeof(w.pose1));
   w.cam = *cam;

@@ -196,4 +196,33 @@ __device__ __forceinline__ float warp_sum(float v)
   return v;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Depth decode shared by update_depth_kernel and the fused RunStep front-ends (DepthFromCode, warping.h:30-69).
+// The reference leaves the summation order of the 1xC * Cx1 product to Eigen; this library fixes it so that the
+// stand-alone UpdateDepth and the fused path agree bit for bit: per float4 chunk a 4-term fma chain starting from 0,
+// then an xor-butterfly over the C/4 chunk sums with offsets NV/2, ..., 1 (what a shuffle-xor all-reduce computes; it
+// is invariant under xor-relabelling of the chunks, so a front-end may hold chunk (j ^ m) in register j).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float chunk_dot(const float4 v, const float4 c)
+{
+  float d = fmaf(v.x, c.x, 0.0f);
+  d = fmaf(v.y, c.y, d);
+  d = fmaf(v.z, c.z, d);
+  return fmaf(v.w, c.w, d);
+}
+template <int NV>
+__device__ __forceinline__ float butterfly_sum(float (&p)[NV])
+{
+#pragma unroll
+  for (int o = NV / 2; o > 0; o >>= 1)
+#pragma unroll
+    for (int j = 0; j < o; ++j) p[j] = __fadd_rn(p[j], p[j + o]);  // pairs (j, j ^ o) of the live prefix
+  return p[0];
+}
+__device__ __forceinline__ float prx_to_depth(float prx, float avg_dpt)
+{
+  return __fsub_rn(__fdiv_rn(avg_dpt, prx), avg_dpt);  // ProxToDepth warping.h:30-35
+}
+
 }  // namespace dfk

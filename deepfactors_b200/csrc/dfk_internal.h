@@ -48,6 +48,11 @@ struct SfmItemDev {
   // partial_begin + (c - first_cta)
   uint32_t first_cta, num_ctas, partial_begin;
   uint32_t flags;  // bit0: bulk-copy (TMA) eligible, bit1: grad1 rows are 8-byte aligned
+  // fused depth decode (ITEM_FLAG_FUSED_DEPTH): `dpt0` then points at prx_orig (what the tile loader stages), the decoded
+  // depth is written to dpt_out; code = code_size floats in device scratch
+  float* dpt_out;
+  uint32_t dpt_out_pitch;
+  const float* code;
   // normalised ray tables in device scratch: xn[0..width), then yn[0..height) (tensor-core kernel)
   const float* ray_tab;
   // relative-pose Jacobians (warping.h:120-134), row-major 6x6; used by the finalize kernel
@@ -55,7 +60,7 @@ struct SfmItemDev {
   float P1[36];
 };
 
-enum : uint32_t { ITEM_FLAG_BULK = 1u, ITEM_FLAG_GRAD_ALIGNED = 2u };
+enum : uint32_t { ITEM_FLAG_BULK = 1u, ITEM_FLAG_GRAD_ALIGNED = 2u, ITEM_FLAG_FUSED_DEPTH = 4u };
 
 // Geometry of the fp32 Gram kernel, shared by host planning code and the kernel.
 template <int C>

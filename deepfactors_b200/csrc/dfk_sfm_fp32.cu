@@ -36,7 +36,8 @@ constexpr int kStages = 3;
 constexpr int kFeWarps = 8;
 constexpr int kFeThreads = kFeWarps * 32;
 static_assert(kTilePixels == kFeThreads, "one front-end thread per tile pixel");
-constexpr int kMaxTab = 1024;  // per-item tables of the normalised ray coordinates (columns / rows)
+constexpr int kMaxTab = 1024;
+constexpr int kMaxCode = 32;  // largest code size of this kernel (fused depth decode keeps the code in shared memory)  // per-item tables of the normalised ray coordinates (columns / rows)
 
 struct TileMeta {
   int nvalid;
@@ -59,6 +60,9 @@ struct ItemSmem {
   const float* grad1;
   uint32_t img0_pitch, img1_pitch, dpt0_pitch, valid0_pitch, jac_pitch, grad1_pitch;
   uint32_t width, height, num_pixels, tile_begin, num_tiles, perm_mul, flags, slot;
+  float* dpt_out;  // fused depth decode (ITEM_FLAG_FUSED_DEPTH): decoded depth goes here, dpt0 stages prx_orig
+  uint32_t dpt_out_pitch;
+  alignas(16) float code[kMaxCode];
 };
 
 template <int C>
@@ -116,7 +120,15 @@ __device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, 
     dst.tile_begin = src.tile_begin; dst.num_tiles = src.num_tiles; dst.perm_mul = src.perm_mul;
     dst.flags = src.flags;
     dst.slot = src.partial_begin + (uint32_t)cta - src.first_cta;
+    dst.dpt_out = src.dpt_out; dst.dpt_out_pitch = src.dpt_out_pitch;
   }
+}
+
+// fused depth decode: the item's latent code -> shared memory (callers sync afterwards)
+__device__ __forceinline__ void load_code(ItemSmem& dst, const SfmItemDev& src, int code_size, int tid, int nthreads)
+{
+  if (src.flags & ITEM_FLAG_FUSED_DEPTH)
+    for (int k = tid; k < code_size; k += nthreads) dst.code[k] = __ldg(src.code + k);
 }
 
 // Issue the bulk copies of global tile g (item `it`) into ring stage `st`.  One thread.
@@ -221,6 +233,7 @@ sfm_step_fp32_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
       if (changed) {
         named_bar_sync(1, kFeThreads);  // everyone finished reading the previous item's params
         load_item(sm.item, items[it], tid, kFeThreads, cta);
+        load_code(sm.item, items[it], C, tid, kFeThreads);
         cur_item = it;
         {
           // normalised ray tables (Reproject's IEEE divisions hoisted out of the pixel loop)
@@ -253,7 +266,17 @@ sfm_step_fp32_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
       if (s < n) {
         const uint32_t p = p0 + s;
         const uint32_t y = p / I.width, x = p - y * I.width;
-        const float d = sm.dpt0[st][s];
+        float d = sm.dpt0[st][s];
+        if (I.flags & ITEM_FLAG_FUSED_DEPTH) {
+          // the stage holds prx_orig: decode the depth exactly as update_depth_kernel does and publish it
+          const float4* row = reinterpret_cast<const float4*>(&sm.jc[st][s * C]);
+          const float4* cod = reinterpret_cast<const float4*>(I.code);
+          float part[C / 4];
+#pragma unroll
+          for (int k4 = 0; k4 < C / 4; ++k4) part[k4] = chunk_dot(row[k4], cod[k4]);
+          d = prx_to_depth(__fadd_rn(d, butterfly_sum<C / 4>(part)), I.avg_dpt);
+          I.dpt_out[(size_t)y * I.dpt_out_pitch + x] = d;
+        }
         const bool tab = (I.width <= kMaxTab) && (I.height <= kMaxTab);
         const float xn = tab ? sm.xn_tab[x] : ray_coord((float)x, I.u0, I.fx);
         const float yn = tab ? sm.yn_tab[y] : ray_coord((float)y, I.v0, I.fy);

@@ -83,8 +83,10 @@ struct ItemSmem {
   const float* jac;
   const float* grad1;
   const float* ray_tab;
-  uint32_t img0_pitch, img1_pitch, dpt0_pitch, valid0_pitch, jac_pitch, grad1_pitch;
+  float* dpt_out;  // fused depth decode: where the decoded depth goes (dpt0 then stages prx_orig)
+  uint32_t img0_pitch, img1_pitch, dpt0_pitch, valid0_pitch, jac_pitch, grad1_pitch, dpt_out_pitch;
   uint32_t width, height, num_pixels, tile_begin, num_tiles, perm_mul, flags, slot, mag_tiles, mag_width;
+  alignas(128) float code[C];  // fused depth decode: the latent code of the item (128-byte aligned: chunk addresses are formed by xor)
 };
 
 struct Smem {
@@ -124,7 +126,9 @@ __device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, 
     dst.jac = src.jac; dst.grad1 = src.grad1; dst.ray_tab = src.ray_tab;
     dst.img0_pitch = src.img0_pitch; dst.img1_pitch = src.img1_pitch; dst.dpt0_pitch = src.dpt0_pitch;
     dst.valid0_pitch = src.valid0_pitch; dst.jac_pitch = src.jac_pitch; dst.grad1_pitch = src.grad1_pitch;
+    dst.dpt_out = src.dpt_out; dst.dpt_out_pitch = src.dpt_out_pitch;
   }
+  if (tid >= 64 && tid < 64 + C && (src.flags & ITEM_FLAG_FUSED_DEPTH)) dst.code[tid - 64] = __ldg(src.code + (tid - 64));
   if (tid == 96) {
     dst.width = src.width; dst.height = src.height; dst.num_pixels = src.num_pixels;
     dst.tile_begin = src.tile_begin; dst.num_tiles = src.num_tiles; dst.perm_mul = src.perm_mul;
@@ -347,7 +351,24 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         if (s < n) {
           const uint32_t y = py, x = pxx;
 #endif
-          const float d = sm.dpt0[st][s];
+          float d = sm.dpt0[st][s];
+          if (I.flags & ITEM_FLAG_FUSED_DEPTH) {
+            // the stage holds prx_orig: decode the depth from this pixel's code-Jacobian row (same arithmetic as
+            // update_depth_kernel: chunk fma chains + xor-butterfly; register j holds chunk j ^ (lane & 7), which the
+            // butterfly does not care about), publish it, and carry on with it
+            const uint32_t src = smem_u32(&sm.jc[st][s * C]) + ((uint32_t)(lane & 7) << 4);
+            const uint32_t cod = smem_u32(I.code) + ((uint32_t)(lane & 7) << 4);
+            float part[C / 4];
+#pragma unroll
+            for (int k4 = 0; k4 < C / 4; ++k4) {
+              float4 v, c;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src ^ ((uint32_t)k4 << 4)));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(cod ^ ((uint32_t)k4 << 4)));
+              part[k4] = chunk_dot(v, c);
+            }
+            d = prx_to_depth(__fadd_rn(d, butterfly_sum<C / 4>(part)), I.avg_dpt);
+            I.dpt_out[(size_t)y * I.dpt_out_pitch + x] = d;
+          }
           const Warped w = warp_ray(xn, yn, d, I.q, I.t, I.fx, I.fy, I.u0, I.v0, I.border, I.ulim, I.vlim, I.min_dpt);
           if (w.valid) {
             ok = true;

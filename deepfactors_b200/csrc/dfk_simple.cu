@@ -342,8 +342,8 @@ update_depth_kernel(const float* __restrict__ code, int width, int height, View 
 #pragma unroll
     for (int o = LPP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
     if (p < area && sub == 0) {
-      const float prxv = __ldg(prx.ptr + (size_t)y * prx.pitch + x) + dot;  // ProxFromCode warping.h:52-59
-      dpt[(size_t)y * dpt_pitch + x] = avg_dpt / prxv - avg_dpt;            // ProxToDepth  warping.h:30-35
+      const float prxv = __fadd_rn(__ldg(prx.ptr + (size_t)y * prx.pitch + x), dot);  // ProxFromCode warping.h:52-59
+      dpt[(size_t)y * dpt_pitch + x] = prx_to_depth(prxv, avg_dpt);  // same order as the fused RunStep front-ends
     }
   }
 }

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define DFK_VERSION 100
+#define DFK_VERSION 101
 
 typedef enum {
   DFK_OK = 0,
@@ -161,6 +161,13 @@ typedef struct {
   float pose1[7];
   DfkCamera cam;
   DfkImage img0, img1, dpt0, valid0, prx0_jac, grad1;
+  /* Optional fused depth decode (PhotometricFactor::UpdateDepthMaps + RunAlignmentStep in one pass,
+   * photometric_factor.cpp:229,331-341): when `code` is not NULL, every pixel's depth is decoded first,
+   *   dpt0(x,y) = avg_dpt / (prx_orig(x,y) + prx0_jac(x,y,:) . code) - avg_dpt      (warping.h:30-69),
+   * written to dpt0 (an OUTPUT in this mode, exactly what dfk_update_depth writes, bit for bit) and used for the warp,
+   * so the code Jacobian is read from HBM once instead of twice.  `code` is a HOST pointer to code_size floats. */
+  DfkImage prx_orig;
+  const float* code;
 } DfkSfmWorkItem;
 
 /* floats per device result record for code size C: [JtJ packed | Jtr | residual | inliers(u32 bits)] */

@@ -170,6 +170,44 @@ def test_sfm_batch_matches_single_calls_and_is_deterministic(torch_mod, mode):
         assert abs(got.residual - ref.residual) <= 1e-5 * max(ref.residual, 1e-12)
 
 
+@pytest.mark.parametrize("cs,w,h,mode", [(32, 320, 240, "auto"), (32, 320, 240, "fp32"), (8, 160, 120, "auto"),
+                                         (16, 200, 96, "auto"), (64, 160, 120, "auto"), (128, 160, 120, "auto"),
+                                         (32, 202, 96, "auto")])
+def test_sfm_fused_depth_decode_equals_update_depth_then_run_step(torch_mod, oracle, cs, w, h, mode):
+    """PhotometricFactor::UpdateDepthMaps + RunAlignmentStep (photometric_factor.cpp:229,331-341) in ONE launch: the
+    decoded depth map and the result records are bit-identical to UpdateDepth followed by RunStep, and the depth agrees
+    with the CPU DepthFromCode (warping.h:30-69) to rounding."""
+    torch = torch_mod
+    from deepfactors_b200.aligners import SfmAligner, UpdateDepth
+    levels = 2
+    pair = synth.make_pair(w, h, cs, levels, seed=40 + cs, code_sigma=0.3)
+    al = SfmAligner(cs, gram_mode=mode)
+    two_step, fused = [], []
+    keep = []
+    for L in pair.levels:
+        dev = upload_level(torch, L, extra_px=0 if w % 4 else 4)
+        dpt_a = torch.zeros_like(dev["dpt0"])
+        UpdateDepth(pair.code, dev["prx_orig"], dev["prx0_jac"], 2.0, dpt_a)
+        dpt_b = torch.full_like(dev["dpt0"], -7.0)  # must be overwritten everywhere by the fused launch
+        va, vb = torch.zeros_like(dev["valid0"]), torch.zeros_like(dev["valid0"])
+        base = dict(pose0=pair.pose0, pose1=pair.pose1, cam=L.cam, img0=dev["img0"], img1=dev["img1"],
+                    prx0_jac=dev["prx0_jac"], grad1=dev["grad1"])
+        two_step.append(dict(base, dpt0=dpt_a, valid0=va))
+        fused.append(dict(base, dpt0=dpt_b, valid0=vb, prx_orig=dev["prx_orig"], code=pair.code))
+        keep.append((dev, dpt_a, dpt_b, va, vb, L))
+    rec_a = al.RunStepBatch(al.make_work_items(two_step)).clone()
+    rec_b = al.RunStepBatch(al.make_work_items(fused)).clone()
+    torch.cuda.synchronize()
+    for dev, dpt_a, dpt_b, va, vb, L in keep:
+        assert torch.equal(dpt_a, dpt_b), "decoded depth differs from UpdateDepth"
+        assert torch.equal(va, vb)
+        ref = oracle.update_depth(pair.code, L.prx_orig, L.prx_jac, 2.0)
+        got = dpt_b.cpu().numpy()
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert torch.equal(rec_a, rec_b), "fused records differ from UpdateDepth + RunStep"
+    assert al.unpack(rec_b)[0].inliers > 0.3 * w * h
+
+
 def test_sfm_evaluate_error_matches_oracle(torch_mod, oracle):
     torch = torch_mod
     from deepfactors_b200.aligners import SfmAligner, SfmAlignerParams, DenseSfmParams

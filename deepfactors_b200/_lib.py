@@ -95,6 +95,7 @@ SYMBOLS = {
     "dfk_update_depth": (C.c_int, [_H, _F, C.c_int, _IMG, _IMG, C.c_float, _IMG]),
     "dfk_sobel_gradients": (C.c_int, [_H, _IMG, _IMG]),
     "dfk_gaussian_blur_down": (C.c_int, [_H, _IMG, _IMG]),
+    "dfk_build_image_pyramid": (C.c_int, [_H, _IMG, _IMG, C.c_int]),
     "dfk_squared_error": (C.c_int, [_H, _IMG, _IMG, _F]),
 }
 

@@ -419,6 +419,16 @@ def GaussianBlurDown(inp, out):
     check(hd.h, lib().dfk_gaussian_blur_down(hd.h, C.byref(i), C.byref(o)))
 
 
+def BuildImagePyramid(imgs, grads=None):
+    """imgs[0] given; fills imgs[1:] by GaussianBlurDown and grads[:] by SobelGradients, all enqueued at once
+    (Frame::FillPyramids, core/mapping/frame.h:80-94)."""
+    hd = _free_handle()
+    n = len(imgs)
+    ia = (DfkImage * n)(*[_image(t) for t in imgs])
+    ga = (DfkImage * n)(*[_image(t, 2) for t in grads]) if grads is not None else None
+    check(hd.h, lib().dfk_build_image_pyramid(hd.h, ia, ga, n))
+
+
 def SquaredError(buf1, buf2) -> float:
     """df::SquaredError (cu_image_proc.cpp:208-242)."""
     hd = _free_handle(buf1.device)

@@ -862,6 +862,22 @@ DfkStatus dfk_gaussian_blur_down(DfkHandle h, const DfkImage* in, const DfkImage
   return DFK_OK;
 }
 
+DfkStatus dfk_build_image_pyramid(DfkHandle h, const DfkImage* imgs, const DfkImage* grads, int levels)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  if (!imgs || levels <= 0) return fail(h, DFK_ERR_INVALID_ARG, "[BuildImagePyramid] null argument / no levels");
+  for (int l = 1; l < levels; ++l) {
+    DfkStatus st = dfk_gaussian_blur_down(h, &imgs[l - 1], &imgs[l]);
+    if (st != DFK_OK) return st;
+  }
+  if (grads)
+    for (int l = 0; l < levels; ++l) {
+      DfkStatus st = dfk_sobel_gradients(h, &imgs[l], &grads[l]);
+      if (st != DFK_OK) return st;
+    }
+  return DFK_OK;
+}
+
 DfkStatus dfk_squared_error(DfkHandle h, const DfkImage* a, const DfkImage* b, float* out)
 {
   if (!h) return DFK_ERR_INVALID_ARG;

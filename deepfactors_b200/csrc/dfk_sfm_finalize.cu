@@ -25,6 +25,7 @@ namespace dfk {
 namespace {
 
 constexpr int kFinWarps = 8;
+constexpr int kFinUnroll = 4;
 
 __device__ __forceinline__ int packed_index(int i, int j, int NP) { return i * NP - (i * (i - 1)) / 2 + (j - i); }
 
@@ -90,15 +91,32 @@ sfm_finalize_kernel(const SfmItemDev* __restrict__ items, const float* __restric
 #pragma unroll
   for (int q = 0; q < EPL; ++q) part[q] = 0.0f;
   unsigned int inl = 0;
-  for (int k = warp; k < np; k += kFinWarps) {
-    const float* Pk = P + (size_t)k * PSTRIDE;
+  // kFinUnroll partials per trip: their loads are independent, so a trip costs one memory round trip instead of
+  // kFinUnroll; the per-trip values are combined in index order, which keeps the summation order fixed
+  for (int k0 = warp; k0 < np; k0 += kFinWarps * kFinUnroll) {
+    float v[kFinUnroll][EPL];
+    unsigned int vi[kFinUnroll];
 #pragma unroll
-    for (int q = 0; q < EPL; ++q)
-      if (act[q]) {
-        if constexpr (TC) part[q] += (Pk[off[q][0]] + Pk[off[q][1]]) + Pk[off[q][2]];
-        else part[q] += Pk[off[q][0]];
+    for (int u = 0; u < kFinUnroll; ++u) {
+      const int k = k0 + u * kFinWarps;
+      const bool on = k < np;
+      const float* Pk = P + (size_t)(on ? k : 0) * PSTRIDE;
+#pragma unroll
+      for (int q = 0; q < EPL; ++q) {
+        v[u][q] = 0.0f;
+        if (on && act[q]) {
+          if constexpr (TC) v[u][q] = (Pk[off[q][0]] + Pk[off[q][1]]) + Pk[off[q][2]];
+          else v[u][q] = Pk[off[q][0]];
+        }
       }
-    if (unit == C && lane == 0) inl += reinterpret_cast<const unsigned int*>(Pk)[INL_OFF];
+      vi[u] = (on && unit == C && lane == 0) ? reinterpret_cast<const unsigned int*>(Pk)[INL_OFF] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kFinUnroll; ++u) {
+#pragma unroll
+      for (int q = 0; q < EPL; ++q) part[q] += v[u][q];
+      inl += vi[u];
+    }
   }
 #pragma unroll
   for (int q = 0; q < EPL; ++q) red[warp][q * 32 + lane] = part[q];

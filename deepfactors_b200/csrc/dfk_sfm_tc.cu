@@ -56,7 +56,10 @@ constexpr int OP_THREADS = 256;       // warps 8-10: operand group A, 11: contro
 constexpr int THREADS = OP_THREADS + FE_GROUPS * FE_THREADS;
 constexpr int NB = 48;           // MMA N (39 used)
 constexpr int MM = 128;          // MMA M (78 used)
-constexpr int kFlushTiles = 8;   // TMEM accumulation chain length (tiles)
+#ifndef DFK_FLUSH_TILES
+#define DFK_FLUSH_TILES 8
+#endif
+constexpr int kFlushTiles = DFK_FLUSH_TILES;  // TMEM accumulation chain length (tiles)
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t A_COL = 0;    // [0,128): two 64-column halves of A
 constexpr uint32_t D_COL = 128;  // [128,176), [176,224): two accumulators

@@ -29,6 +29,7 @@
 #include <array>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -238,6 +239,38 @@ public:
                                               &s0, &v0, &jc, &g1, r.JtJ.coeff().data(), r.Jtr.data(), &r.residual,
                                               &inl));
     r.inliers = static_cast<std::size_t>(inl);
+    return r;
+  }
+
+  // UpdateDepth + RunStep in one launch (what PhotometricFactor does back to back: UpdateDepthMaps,
+  // photometric_factor.cpp:331-341, then RunAlignmentStep :267-274): dpt0 is decoded from prx_orig0 + prx0_jac * code0
+  // inside the kernel, written to dpt0 (an output here) and used for the warp; the code Jacobian is read once.
+  template <typename SE3T, typename CodeT, typename CamT, typename ImageBuffer, typename GradBuffer>
+  ReductionItem RunStepDecodeDepth(const SE3T& pose0, const SE3T& pose1, const CodeT& code0, const CamT& cam,
+                                   const ImageBuffer& img0, const ImageBuffer& img1, const ImageBuffer& prx_orig0,
+                                   ImageBuffer& dpt0, ImageBuffer& valid0, const ImageBuffer& prx0_jac,
+                                   const GradBuffer& grad1)
+  {
+    DfkSfmWorkItem w{};
+    for (int k = 0; k < 7; ++k) {
+      w.pose0[k] = pose0.data()[k];
+      w.pose1[k] = pose1.data()[k];
+    }
+    w.cam = detail::Cam(cam);
+    w.img0 = detail::View(img0, 1); w.img1 = detail::View(img1, 1); w.dpt0 = detail::View(dpt0, 1);
+    w.valid0 = detail::View(valid0, 1); w.prx0_jac = detail::View(prx0_jac, CS); w.grad1 = detail::View(grad1, 2);
+    w.prx_orig = detail::View(prx_orig0, 1);
+    w.code = code0.data();
+    std::vector<float> rec(DFK_SFM_RECORD_FLOATS(CS));
+    detail::Check(h_.get(), dfk_sfm_run_step_batch_host(h_.get(), &w, 1, CS, rec.data()));
+    ReductionItem r;
+    constexpr int NP = 12 + CS, NH = NP * (NP + 1) / 2;
+    for (int k = 0; k < NH; ++k) r.JtJ.coeff().data()[k] = rec[k];
+    for (int k = 0; k < NP; ++k) r.Jtr.data()[k] = rec[NH + k];
+    r.residual = rec[NH + NP];
+    uint32_t bits;
+    std::memcpy(&bits, &rec[NH + NP + 1], 4);
+    r.inliers = bits;
     return r;
   }
 

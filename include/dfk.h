@@ -235,6 +235,12 @@ DfkStatus dfk_update_depth(DfkHandle h, const float* code, int code_size, const 
 DfkStatus dfk_sobel_gradients(DfkHandle h, const DfkImage* img, const DfkImage* grad);
 /* df::GaussianBlurDown (cu_image_proc.h:31-33, cu_image_proc.cpp:134-184). Asynchronous. */
 DfkStatus dfk_gaussian_blur_down(DfkHandle h, const DfkImage* in, const DfkImage* out);
+/* The image half of Frame::FillPyramids / BuildKeyframe (core/mapping/frame.h:80-94, mapper.cpp:935-949):
+ * imgs[0] is the input; imgs[l] = GaussianBlurDown(imgs[l-1]) and, when grads != NULL, grads[l] =
+ * SobelGradients(imgs[l]) for every level.  2*levels-1 launches enqueued back to back on the handle's stream, no host
+ * synchronization (the reference synchronizes after each and re-uploads the kernel taps with cudaMemcpyToSymbol,
+ * cu_image_proc.cpp:103-112,174-183). */
+DfkStatus dfk_build_image_pyramid(DfkHandle h, const DfkImage* imgs, const DfkImage* grads, int levels);
 /* df::SquaredError (cu_image_proc.h:35-39, cu_image_proc.cpp:190-242). Synchronous. */
 DfkStatus dfk_squared_error(DfkHandle h, const DfkImage* a, const DfkImage* b, float* out);
 

@@ -108,6 +108,19 @@ int main()
                       &res6f, &inl6f);
   EXPECT(r6.inliers == inl6f);
 
+  // fused depth decode: with a zero code the decoded depth is avg/prx_orig - avg == dpt0, so the fused call must
+  // reproduce the plain RunStep (same inliers; same sums up to the 1-ulp difference between the two depth formulas)
+  {
+    std::vector<float> prx(W * H);
+    for (int i = 0; i < W * H; ++i) prx[i] = 2.0f / (dpt0[i] + 2.0f);
+    DeviceImage<float> d_prx(W, H), d_dout(W, H), d_vld2(W, H);
+    d_prx.copyFrom(prx.data());
+    auto po = d_prx.view(), dout = d_dout.view(), v2 = d_vld2.view();
+    auto fused = aligner.RunStepDecodeDepth(pose0, pose1, code, cam, i0, i1, po, dout, v2, jc, gr);
+    EXPECT(std::llabs((long long)fused.inliers - (long long)gpu.inliers) <= 8);
+    EXPECT(std::fabs(fused.residual - gpu.residual) <= 1e-3f * gpu.residual);
+  }
+
   // CameraTracker::TrackFrame's loop as one device-side call: a single level, 8 Gauss-Newton iterations starting at
   // pose1 must not increase the mean Huber-weighted residual, and moves the pose
   {

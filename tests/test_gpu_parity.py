@@ -366,6 +366,25 @@ def test_image_proc_matches_oracle_and_opencv(torch_mod, oracle, golden):
         assert np.all(np.abs(out.cpu().numpy() - ref) <= 1e-5 * np.abs(ref) + 1e-6)
 
 
+def test_build_image_pyramid_matches_per_level_calls(torch_mod, oracle, golden):
+    """Frame::FillPyramids (frame.h:80-94): blur-down chain + Sobel per level in one enqueue == the oracle's chain"""
+    torch = torch_mod
+    from deepfactors_b200.aligners import BuildImagePyramid
+    img = golden["gray_1047"].astype(np.float32) * np.float32(1 / 255.0)
+    levels = 4
+    imgs = [pitched(torch, img, 3)] + [torch.zeros((240 >> l, 320 >> l), device="cuda") for l in range(1, levels)]
+    grads = [torch.zeros((240 >> l, 320 >> l, 2), device="cuda") for l in range(levels)]
+    BuildImagePyramid(imgs, grads)
+    torch.cuda.synchronize()
+    ref = img
+    for l in range(levels):
+        if l:
+            ref = oracle.gaussian_blur_down(ref)
+        assert np.abs(imgs[l].cpu().numpy() - ref).max() <= 1e-6
+        g = oracle.sobel_gradients(imgs[l].cpu().numpy())
+        assert np.array_equal(grads[l].cpu().numpy(), g)
+
+
 def test_error_reporting_is_loud(torch_mod):
     torch = torch_mod
     from deepfactors_b200 import _lib

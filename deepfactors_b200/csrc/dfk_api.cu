@@ -393,7 +393,8 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     DFK_CUDA(h, ensure(&h->codes_dev, &h->codes_cap, (size_t)n * code_size), "[SfmAligner::RunStep] scratch allocation failed");
     h->codes_host.assign((size_t)n * code_size, 0.0f);
   }
-  DfkStatus st = build_items(h, items, n, code_size, tile_px, tc ? 2 * h->num_sms : h->num_sms,
+  const int ctas_per_sm = tc ? 2 : (wide ? 1 : sfm_fp32_ctas_per_sm(code_size));
+  DfkStatus st = build_items(h, items, n, code_size, tile_px, ctas_per_sm * h->num_sms,
                              tc ? h->ray_tabs_dev : nullptr, h->codes_dev, &plan);
   if (st != DFK_OK) return st;
   if (any_fused)

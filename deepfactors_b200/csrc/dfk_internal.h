@@ -109,6 +109,9 @@ cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan
                           float* partials_dev, cudaStream_t stream, cudaEvent_t ev_start = nullptr,
                           cudaEvent_t ev_stop = nullptr);
 size_t sfm_partial_floats(int code_size);
+// resident CTAs per SM of the fp32 kernel: at C = 8 a CTA is 11 warps and ~60 KB of shared memory, two fit (the front-end
+// is latency-bound, so the second CTA nearly doubles the throughput); from C = 16 on the register budget allows one
+constexpr int sfm_fp32_ctas_per_sm(int code_size) { return code_size <= 8 ? 2 : 1; }
 bool sfm_fp32_supported(int code_size);
 int sfm_max_ctas();  // grid size of the persistent kernel on the current device
 

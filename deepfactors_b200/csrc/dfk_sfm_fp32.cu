@@ -178,7 +178,7 @@ __device__ __forceinline__ void coop_tile_loads(Smem<C>& sm, const ItemSmem& I, 
 }
 
 template <int C>
-__global__ void __launch_bounds__((kFeWarps + SfmCfg<C>::NBLK) * 32, 1)
+__global__ void __launch_bounds__((kFeWarps + SfmCfg<C>::NBLK) * 32, sfm_fp32_ctas_per_sm(C))
 sfm_step_fp32_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_tiles, float* __restrict__ partials)
 {
   using Cfg = SfmCfg<C>;

@@ -10,21 +10,26 @@
 //   M = 128 rows) and B = h (39 of N = 48 columns), one tcgen05.mma.kind::tf32 per 8 pixels yields
 //   HH = sum h h^T and LH = sum l h^T;  G = HH + LH + LH^T  drops only the l*l terms (~2^-22).
 //
-//   Per CTA (256 threads, 2 CTAs / SM, 256 TMEM columns each):
-//     warps 4-7  front-end : one thread per pixel of a 128-pixel tile: exact-order validity chain, bilinear
-//                            gathers, Jacobian row, Huber; valid pixels compacted; per-pixel scalars
-//                            (s = w*e, w*a[6], w*diff) + the pixel's slot id go to shared memory.
-//     warps 0-2  operand   : lane = feature row.  warp 0: h of the 32 code features (raw s*jc; the
-//                            tensor core truncates), also written K-major to shared memory as B;
-//                            warp 1: l of the code features; warp 2: h and l of the 7 pose/residual
-//                            features.  A goes registers -> TMEM with tcgen05.st (lane = row, column =
-//                            pixel); the code Jacobian rows come from the TMA-staged tile with one
-//                            conflict-free LDS per pixel (lane = code dimension).
-//     warp 3     control   : lane 0 issues the MMAs (A from TMEM, B from shared memory through a
-//                            K-major no-swizzle descriptor) and the tcgen05.commit arrivals.
-//   The fp32 accumulator in TMEM adds with truncation (measured: ~ -2^-24 relative per k-step), so a
-//   chain is cut every kFlushTiles tiles: the operand warps pull the finished chain out of TMEM
-//   (tcgen05.ld) and add it to register accumulators in round-to-nearest fp32.
+//   Per CTA (512 threads, 2 CTAs / SM, 256 TMEM columns each; register budgets by setmaxnreg):
+//     warps 0-7   front-end : two groups of 4 warps that alternate tiles; one thread per pixel of a 128-pixel tile:
+//                             (optional depth decode,) exact-order validity chain, bilinear gathers, Jacobian row,
+//                             Huber.  Each warp owns one 32-pixel block: valid pixels are compacted warp-locally and
+//                             the staged code-Jacobian row of a valid pixel is scaled by s = w*e and moved to its rank
+//                             IN PLACE in the ring stage; w*a[6], w*diff go to shared memory (feat).
+//     warps 8-10, operand   : two groups (A, B) of 3 warps, lane = feature row; group g builds blocks g and g+2 of
+//           12-14             every tile.  ow 0: h of the 32 code features (the raw scaled values; the tensor core
+//                             truncates), also written K-major to shared memory as B; ow 1: l of the code features;
+//                             ow 2: h and l of the 7 pose/residual features.  A goes registers -> TMEM with
+//                             tcgen05.st.32x32b.x32 (lane = row, column = pixel); the code rows are read with one
+//                             conflict-free LDS per pixel (lane = code dimension).  Group A also drains the chains.
+//     warp 11     control   : lane 0 issues the MMAs (A from TMEM, B from shared memory through a K-major no-swizzle
+//                             descriptor), the tcgen05.commit arrivals, and allocates TMEM.
+//     warp 15     producer  : lane 0 issues the cp.async.bulk copies of a tile as soon as its ring stage is free.
+//   The fp32 accumulator in TMEM adds with truncation (measured: ~ -2^-24 relative per k-step), so a chain is cut every
+//   kFlushTiles tiles: operand group A pulls the finished chain out of TMEM (tcgen05.ld) and adds it in round-to-nearest
+//   fp32 to the CTA's partial in global memory (single writer per address, program order => reproducible).
+//   Experiment switches (-DDFK_EXP_NOGEOM / NOCOMPACT / NOOPBUILD / NOMMA / NODRAIN: wrong results, informative
+//   times) and phase timers (-DDFK_TC_TIMERS + env DFK_TC_DEBUG=1) are kept for the roofline accounting in DESIGN.md.
 //
 // Tile staging (cp.async.bulk row segments into a 4-deep ring), the static tile->CTA assignment, the
 // in-item tile permutation, the per-CTA partials and the wide deterministic finalize are those of the

@@ -8,6 +8,9 @@
 //   layout 2: K-major,  no swizzle     addr(f,k) = (f/8)*(KT*32) + (k/4)*128 + (f%8)*16 + (k%4)*4
 //   layout 3: K-major,  SWIZZLE_128B   addr(f,k) = (k/32)*KBLK + (f/8)*1024 + (f%8)*128 + (((k%32)/4) ^ (f%8))*16 + (k%4)*4
 //             (only features 0..79 are stored; K blocks 10 KB apart, so D rows 80..127 are junk by construction)
+// Measured on B200 (sm_100a, CUDA 12.9): the SS form works for K-major operands, no swizzle and SWIZZLE_128B alike
+// (error 1e-5 = tf32 truncation), including start addresses advanced by 32 bytes per k-step inside the swizzle atom, K
+// blocks 10 KB apart and LBO = 0 / 16 / 1024 (ignored); every MN-major variant (a_major = b_major = 1) WRITES ZEROS.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -o umma_probe_mn umma_probe_mn.cu
 #include <cuda_runtime.h>
 #include <math.h>

@@ -126,6 +126,54 @@ def test_sfm_identity_pose_all_pixels_inliers(torch_mod, oracle):
         compare_step(g, o32, o64, f"identity gram={mode}")
 
 
+@pytest.mark.parametrize("w,h,cs", [(33, 7, 32), (5, 5, 8), (64, 5, 32), (129, 6, 16), (12, 9, 64), (257, 5, 128)])
+def test_sfm_degenerate_image_sizes(torch_mod, oracle, w, h, cs):
+    """ragged / tiny inputs: fewer pixels than one tile, rows shorter than a TMA segment, odd widths (cooperative
+    staging instead of bulk copies), items that give most CTAs nothing to do"""
+    torch = torch_mod
+    from deepfactors_b200.aligners import SfmAligner
+    pair = synth.make_pair(w, h, cs, 1, seed=w * h, identity_pose=True)
+    L = pair.levels[0]
+    dev = upload_level(torch, L, extra_px=1)
+    v_cpu = np.zeros((h, w), dtype=np.float32)
+    o32 = oracle.sfm_run_step(pair.pose0, pair.pose1, L.cam, L.img0, L.img1, L.dpt0, v_cpu, L.prx_jac, L.grad1)
+    o64 = oracle.sfm_run_step(pair.pose0, pair.pose1, L.cam, L.img0, L.img1, L.dpt0, None, L.prx_jac, L.grad1,
+                              precision="f64")
+    for mode in (("fp32", "tf32x3") if cs == 32 else ("auto",)):
+        dev["valid0"].zero_()
+        al = SfmAligner(cs, gram_mode=mode)
+        g = al.RunStep(pair.pose0, pair.pose1, pair.code, L.cam, dev["img0"], dev["img1"], dev["dpt0"], None,
+                       dev["valid0"], dev["prx0_jac"], dev["grad1"])
+        assert g.inliers == o32.inliers == int(v_cpu.sum())
+        assert np.array_equal(dev["valid0"].cpu().numpy(), v_cpu)
+        if o32.inliers:
+            compare_step(g, o32, o64, f"{w}x{h} C={cs} gram={mode}")
+        else:
+            assert g.residual == 0.0 and not np.any(g.JtJ)
+
+
+def test_sfm_batch_of_mixed_sizes_matches_single_calls(torch_mod):
+    """one launch over items of very different sizes (a 320x240 level next to 7-row and 5x5 images) == per-item calls"""
+    torch = torch_mod
+    from deepfactors_b200.aligners import SfmAligner
+    al = SfmAligner(32)
+    items, singles = [], []
+    for k, (w, h) in enumerate([(320, 240), (33, 7), (5, 5), (160, 120), (64, 5), (31, 33)]):
+        pair = synth.make_pair(w, h, 32, 1, seed=60 + k, identity_pose=(k % 2 == 1))
+        L = pair.levels[0]
+        dev = upload_level(torch, L)
+        items.append(dict(pose0=pair.pose0, pose1=pair.pose1, cam=L.cam, **{k2: dev[k2] for k2 in (
+            "img0", "img1", "dpt0", "valid0", "prx0_jac", "grad1")}))
+        singles.append(al.RunStep(pair.pose0, pair.pose1, pair.code, L.cam, dev["img0"], dev["img1"], dev["dpt0"], None,
+                                  dev["valid0"], dev["prx0_jac"], dev["grad1"]))
+    recs = al.unpack(al.RunStepBatch(al.make_work_items(items)))
+    for got, ref in zip(recs, singles):
+        assert got.inliers == ref.inliers
+        scale = max(np.abs(ref.JtJ).max(), 1e-30)
+        assert np.abs(got.JtJ - ref.JtJ).max() <= 1e-5 * scale
+        assert abs(got.residual - ref.residual) <= 1e-5 * max(ref.residual, 1e-12)
+
+
 def test_sfm_no_overlap_gives_zero_system(torch_mod):
     """zero overlap: inliers == 0, zero Hessian (photometric_factor.cpp:279-282 then sets residual = inf)"""
     torch = torch_mod

@@ -109,6 +109,30 @@ def test_c128_full_size_properties():
     assert np.abs(sub.toDenseMatrix() - H[:44, :44]).max() <= 2e-5 * scale
 
 
+def test_large_image_1280x960_properties():
+    """four times BASELINE's largest level (1280x960, C=32): inliers == mask, reproducible, engines agree"""
+    import torch
+    from deepfactors_b200.aligners import SfmAligner
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    pair = synth.make_pair(1280, 960, 32, 1, seed=8)
+    L = pair.levels[0]
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in dict(
+        img0=L.img0, img1=L.img1, dpt0=L.dpt0, prx0_jac=L.prx_jac, grad1=L.grad1).items()}
+    d["valid0"] = torch.zeros_like(d["img0"])
+    d["cam"] = L.cam
+    res = {}
+    for mode in ("tf32x3", "fp32"):
+        al = SfmAligner(32, gram_mode=mode)
+        d["valid0"].zero_()
+        a, b = run(al, pair, d), run(al, pair, d)
+        assert np.array_equal(a.JtJ, b.JtJ) and a.inliers == int((d["valid0"] == 1).sum()) > 500000
+        res[mode] = a
+    assert res["fp32"].inliers == res["tf32x3"].inliers
+    scale = np.abs(res["fp32"].JtJ).max()
+    assert np.abs(res["fp32"].JtJ - res["tf32x3"].JtJ).max() <= 2e-5 * scale
+
+
 def test_gram_engines_agree_on_the_full_pyramid(full_pair):
     from deepfactors_b200.aligners import SfmAligner
     pair, dev = full_pair

@@ -144,6 +144,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def host_threads() -> int:
+    """every host core this process may run on -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_eval_seconds(orc, pair, threads):
     t0 = time.perf_counter()
     for L in pair.levels:
@@ -158,7 +166,7 @@ def cpu_baseline(budget_s: float, code_sigma: float = 0.0, identity_pose: bool =
     from oracle import oracle as orc
     orc.build()
     pair = synth.make_pair(W0, H0, CS, LEVELS, seed=0, code_sigma=code_sigma, identity_pose=identity_pose)
-    threads = orc.omp_max_threads()
+    threads = host_threads()
     cpu_eval_seconds(orc, pair, threads)  # warm-up
     ts = []
     t_end = time.perf_counter() + budget_s
@@ -180,7 +188,7 @@ def run_reference_arm(args):
     from oracle import oracle as orc
     orc.build()
     pair = synth.make_pair(W0, H0, CS, LEVELS, seed=0, code_sigma=args.code_sigma, identity_pose=args.identity_pose)
-    threads = orc.omp_max_threads()
+    threads = host_threads()
     for _ in range(max(1, min(args.warmup, 3))):
         cpu_eval_seconds(orc, pair, threads)
     steps = max(1, args.steps)

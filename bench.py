@@ -175,7 +175,14 @@ def cpu_baseline(budget_s: float, code_sigma: float = 0.0, identity_pose: bool =
     ts.sort()
     reps = len(ts)
     med = ts[len(ts) // 2]
+    # also the reference test's own structure -- one thread, x outer / y inner (ut_sfmaligner.cpp:303-315)
+    t0 = time.perf_counter()
+    for L in pair.levels:
+        orc.sfm_run_step(pair.pose0, pair.pose1, L.cam, L.img0, L.img1, L.dpt0, None, L.prx_jac, L.grad1, loop_order=0)
+    single = 1.0 / (time.perf_counter() - t0)
     return {"value": 1.0 / med, "unit": "evals/s", "cores": threads, "kind": "port",
+            "single_thread_reference_loop_order": {"value": single, "unit": "evals/s", "cores": 1,
+                                                   "sample": "1 evaluation, x outer / y inner as ut_sfmaligner.cpp:303-315"},
             "sample": f"{reps} evaluations of one 640x480 4-level C=32 pair (median of {reps}, "
                       f"{sum(ts):.1f} s of CPU work), oracle fp32 OpenMP row-major"}, pair
 

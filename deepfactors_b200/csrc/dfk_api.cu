@@ -70,6 +70,18 @@ DfkStatus fail(DfkHandle h, DfkStatus s, const std::string& msg)
   return s;
 }
 
+// out-of-memory exit of an extern "C" entry point (never throws itself)
+DfkStatus oom(DfkHandle h) noexcept
+{
+  if (h) {
+    try {
+      h->err = "out of host memory";
+    } catch (...) {
+    }
+  }
+  return DFK_ERR_NOMEM;
+}
+
 DfkStatus cuda_fail(DfkHandle h, cudaError_t e, const char* what)
 {
   // message format of vc::CUDAException thrown from CudaCheckLastError (launch_utils.h:26-32)
@@ -178,6 +190,15 @@ bool img_ok(const DfkImage* im, uint32_t w, uint32_t h, uint32_t floats_per_px)
          im->pitch_bytes >= (size_t)w * floats_per_px * 4;
 }
 
+// The validity window comes from the camera (PixelValid: u < cam.width - border, pinhole_camera_impl.h:102-108) while the
+// bilinear taps index the images: a camera larger than the level it is used with (e.g. a level-0 camera with level-1
+// buffers) would read outside them.  The reference has no such check (it would read out of bounds); here it is an
+// argument error.
+bool cam_ok(const DfkCamera* cam, uint32_t w, uint32_t h)
+{
+  return cam && cam->width <= (float)w && cam->height <= (float)h && cam->width >= 0.0f && cam->height >= 0.0f;
+}
+
 View view_of(const DfkImage* im) { return View{static_cast<const float*>(im->ptr), (uint32_t)(im->pitch_bytes / 4)}; }
 
 bool aligned(const void* p, size_t a) { return reinterpret_cast<uintptr_t>(p) % a == 0; }
@@ -221,19 +242,25 @@ template <typename T>
 cudaError_t ensure(T** ptr, size_t* cap, size_t need)
 {
   if (*cap >= need) return cudaSuccess;
+  const size_t old_cap = *cap;
+  // cudaFree synchronises the device, so work still running on the stream has finished with the old buffer
   if (*ptr) cudaFree(*ptr);
   *ptr = nullptr;
   *cap = 0;
-  size_t n = std::max(need, (*cap) * 2);
+  size_t n = std::max(need, old_cap * 2);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(ptr), n * sizeof(T));
   if (e == cudaSuccess) *cap = n;
   return e;
 }
 
+// floor(2^32 / b) for div_magic on the device (b == 1: 2^32 - 1, which the single correction step makes exact)
+uint32_t tc_magic(uint32_t b) { return b <= 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / b); }
+
+// tile_px == 0: block decomposition of the tensor-core kernel (see SfmItemDev::tc_*)
 DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, int tile_px, int max_ctas,
-                      float* ray_tabs, const float* codes_dev, SfmLaunchPlan* plan)
+                      const float* codes_dev, SfmLaunchPlan* plan)
 {
-  size_t ray_cursor = 0;
+  const bool tc = (tile_px == 0);
   const DfkDenseSfmParams& sp = h->params.sfmparams;
   h->items_host.resize(n);
   uint32_t tile_cursor = 0;
@@ -247,6 +274,9 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
       return fail(h, DFK_ERR_INVALID_ARG,
                   "[SfmAligner::RunStep] inconsistent image views (size, pitch or null pointer) in work item " +
                       std::to_string(i));
+    if (!cam_ok(&w.cam, W, H))
+      return fail(h, DFK_ERR_INVALID_ARG,
+                  "[SfmAligner::RunStep] camera viewport larger than the image views in work item " + std::to_string(i));
     float p10[7];
     relative_pose(w.pose1, w.pose0, p10, d.P1, d.P0);  // RelativePose(pose1, pose0, J_pose1, J_pose0)
     for (int k = 0; k < 4; ++k) d.q[k] = p10[k];
@@ -278,18 +308,35 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
       memcpy(h->codes_host.data() + (size_t)i * code_size, w.code, sizeof(float) * code_size);
     }
     d.width = W; d.height = H; d.num_pixels = W * H;
-    d.num_tiles = (d.num_pixels + tile_px - 1) / tile_px;
-    d.ray_tab = ray_tabs ? ray_tabs + ray_cursor : nullptr;
-    ray_cursor += (size_t)W + H;
+    d.ray_tab = nullptr;
+    d.tc_ph = d.tc_ngroups = d.tc_npatches = 0;
+    d.tc_mag_ph = d.tc_mag_np = d.tc_mag_ng = 0;
+    if (tc) {
+      const uint32_t nstrips = (W + kTcBlockPixels - 1) / kTcBlockPixels;
+      d.tc_ngroups = (H + 31) / 32;
+      d.tc_ph = (H + d.tc_ngroups - 1) / d.tc_ngroups;  // <= 32 rows per patch, the last patch of a strip may run past H
+      d.tc_npatches = nstrips * d.tc_ngroups;
+      d.num_tiles = d.tc_npatches * d.tc_ph;
+      d.perm_mul = perm_multiplier(d.tc_npatches);
+      d.tc_mag_ph = tc_magic(d.tc_ph);
+      d.tc_mag_np = tc_magic(d.tc_npatches);
+      d.tc_mag_ng = tc_magic(d.tc_ngroups);
+      d.mag_tiles = 0;
+    } else {
+      d.num_tiles = (d.num_pixels + tile_px - 1) / tile_px;
+      d.perm_mul = perm_multiplier(d.num_tiles);
+      d.mag_tiles = (uint32_t)((1ull << 32) / d.num_tiles);
+    }
     d.tile_begin = tile_cursor;
     tile_cursor += d.num_tiles;
-    d.perm_mul = perm_multiplier(d.num_tiles);
-    d.mag_tiles = (uint32_t)((1ull << 32) / d.num_tiles);
     d.mag_width = (uint32_t)((1ull << 32) / W);
     d.flags = 0;
-    const bool bulk = (W % 4 == 0) && aligned(d.img0, 16) && aligned(d.dpt0, 16) && aligned(d.jac, 16) &&
-                      (d.img0_pitch % 4 == 0) && (d.dpt0_pitch % 4 == 0) && (d.jac_pitch % 4 == 0) &&
-                      (code_size % 4 == 0);
+    // bulk copies (TMA engine) need 16-byte aligned sources and sizes; the tensor-core kernel stages only the code
+    // Jacobian that way (row segments of 32 pixels), the other kernels stage img0 / dpt0 as well
+    const bool bulk = tc ? (aligned(d.jac, 16) && (d.jac_pitch % 4 == 0) && (code_size % 4 == 0))
+                         : ((W % 4 == 0) && aligned(d.img0, 16) && aligned(d.dpt0, 16) && aligned(d.jac, 16) &&
+                            (d.img0_pitch % 4 == 0) && (d.dpt0_pitch % 4 == 0) && (d.jac_pitch % 4 == 0) &&
+                            (code_size % 4 == 0));
     if (bulk) d.flags |= ITEM_FLAG_BULK;
     if (aligned(d.grad1, 8) && d.grad1_pitch % 2 == 0) d.flags |= ITEM_FLAG_GRAD_ALIGNED;
     if (fused) d.flags |= ITEM_FLAG_FUSED_DEPTH;
@@ -381,12 +428,7 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
                     std::to_string(code_size));
   DeviceGuard guard(h->device);
   SfmLaunchPlan plan;
-  if (tc) {
-    size_t ray_floats = 0;
-    for (int i = 0; i < n; ++i) ray_floats += (size_t)items[i].img0.width + items[i].img0.height;
-    DFK_CUDA(h, ensure(&h->ray_tabs_dev, &h->ray_tabs_cap, ray_floats), "[SfmAligner::RunStep] scratch allocation failed");
-  }
-  const int tile_px = tc ? kTcTilePixels : (wide ? sfm_wide_tile_pixels(code_size) : kTilePixels);
+  const int tile_px = tc ? 0 : (wide ? sfm_wide_tile_pixels(code_size) : kTilePixels);
   bool any_fused = false;
   for (int i = 0; i < n; ++i) any_fused = any_fused || items[i].code != nullptr;
   if (any_fused) {
@@ -394,8 +436,7 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     h->codes_host.assign((size_t)n * code_size, 0.0f);
   }
   const int ctas_per_sm = tc ? 2 : (wide ? 1 : sfm_fp32_ctas_per_sm(code_size));
-  DfkStatus st = build_items(h, items, n, code_size, tile_px, ctas_per_sm * h->num_sms,
-                             tc ? h->ray_tabs_dev : nullptr, h->codes_dev, &plan);
+  DfkStatus st = build_items(h, items, n, code_size, tile_px, ctas_per_sm * h->num_sms, h->codes_dev, &plan);
   if (st != DFK_OK) return st;
   if (any_fused)
     DFK_CUDA(h, cudaMemcpyAsync(h->codes_dev, h->codes_host.data(), sizeof(float) * (size_t)n * code_size,
@@ -414,9 +455,8 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     if (ps != DFK_OK) return ps;
   }
   if (tc) {
-    DFK_CUDA(h, launch_sfm_tc(h->items_dev, plan, h->ray_tabs_dev, h->partials_dev, h->stream, ev0, ev1),
+    DFK_CUDA(h, launch_sfm_tc(h->items_dev, plan, h->partials_dev, h->stream, ev0, ev1),
              "[SfmAligner::RunStep] kernel launch failed");
-    h->launches += 1;  // ray-table kernel
   } else if (wide) {
     DFK_CUDA(h, launch_sfm_wide(code_size, h->items_dev, plan, h->partials_dev, h->stream, ev0, ev1),
              "[SfmAligner::RunStep] kernel launch failed");
@@ -456,171 +496,226 @@ int dfk_sfm_supports_code_size(int code_size)
 
 DfkStatus dfk_create(int device, DfkHandle* out)
 {
-  if (!out) return DFK_ERR_INVALID_ARG;
-  *out = nullptr;
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) return DFK_ERR_CUDA;
-  if (device < 0) {
-    if (cudaGetDevice(&device) != cudaSuccess) return DFK_ERR_CUDA;
+  try {
+    if (!out) return DFK_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return DFK_ERR_CUDA;
+    if (device < 0) {
+      if (cudaGetDevice(&device) != cudaSuccess) return DFK_ERR_CUDA;
+    }
+    if (device >= count) return DFK_ERR_INVALID_ARG;
+    DfkContext* h = new (std::nothrow) DfkContext();
+    if (!h) return DFK_ERR_NOMEM;
+    h->device = device;
+    h->params.sfmparams = DfkDenseSfmParams{0.1f, 1000.f, 2.0f, 0.0f, 2};
+    h->params.step_threads = 32; h->params.step_blocks = 11; h->params.eval_threads = 224; h->params.eval_blocks = 66;
+    DeviceGuard guard(device);
+    bool ok = true;
+    ok = ok && cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    h->stream = h->own_stream;
+    ok = ok && cudaMalloc((void**)&h->simple_scratch, sizeof(float) * kSimpleScratchFloats) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->counter, sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->out_dev, sizeof(float) * 32) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&h->code_dev, sizeof(float) * 256) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&h->out_host, sizeof(float) * 32) == cudaSuccess;
+    ok = ok && cudaMemset(h->counter, 0, sizeof(unsigned int)) == cudaSuccess;
+    if (!ok) {
+      dfk_destroy(h);
+      return DFK_ERR_CUDA;
+    }
+    *out = h;
+    return DFK_OK;
+  } catch (...) {
+    return DFK_ERR_NOMEM;
   }
-  if (device >= count) return DFK_ERR_INVALID_ARG;
-  DfkContext* h = new (std::nothrow) DfkContext();
-  if (!h) return DFK_ERR_NOMEM;
-  h->device = device;
-  h->params.sfmparams = DfkDenseSfmParams{0.1f, 1000.f, 2.0f, 0.0f, 2};
-  h->params.step_threads = 32; h->params.step_blocks = 11; h->params.eval_threads = 224; h->params.eval_blocks = 66;
-  DeviceGuard guard(device);
-  bool ok = true;
-  ok = ok && cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
-  ok = ok && cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess;
-  h->stream = h->own_stream;
-  ok = ok && cudaMalloc((void**)&h->simple_scratch, sizeof(float) * kSimpleScratchFloats) == cudaSuccess;
-  ok = ok && cudaMalloc((void**)&h->counter, sizeof(unsigned int)) == cudaSuccess;
-  ok = ok && cudaMalloc((void**)&h->out_dev, sizeof(float) * 32) == cudaSuccess;
-  ok = ok && cudaMalloc((void**)&h->code_dev, sizeof(float) * 256) == cudaSuccess;
-  ok = ok && cudaMallocHost((void**)&h->out_host, sizeof(float) * 32) == cudaSuccess;
-  ok = ok && cudaMemset(h->counter, 0, sizeof(unsigned int)) == cudaSuccess;
-  if (!ok) {
-    dfk_destroy(h);
-    return DFK_ERR_CUDA;
-  }
-  *out = h;
-  return DFK_OK;
 }
 
 DfkStatus dfk_destroy(DfkHandle h)
 {
-  if (!h) return DFK_OK;
-  DeviceGuard guard(h->device);
-  if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-  cudaFree(h->simple_scratch); cudaFree(h->counter); cudaFree(h->out_dev); cudaFree(h->code_dev);
-  cudaFree(h->track_dev);
-  cudaFree(h->codes_dev);
-  if (h->track_host) cudaFreeHost(h->track_host);
-  cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev); cudaFree(h->ray_tabs_dev);
-  if (h->out_host) cudaFreeHost(h->out_host);
-  if (h->records_host) cudaFreeHost(h->records_host);
-  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
-  if (h->own_stream) cudaStreamDestroy(h->own_stream);
-  delete h;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_OK;
+    DeviceGuard guard(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    cudaFree(h->simple_scratch); cudaFree(h->counter); cudaFree(h->out_dev); cudaFree(h->code_dev);
+    cudaFree(h->track_dev);
+    cudaFree(h->codes_dev);
+    if (h->track_host) cudaFreeHost(h->track_host);
+    cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev); cudaFree(h->ray_tabs_dev);
+    if (h->out_host) cudaFreeHost(h->out_host);
+    if (h->records_host) cudaFreeHost(h->records_host);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_set_stream(DfkHandle h, void* cuda_stream)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  h->stream = static_cast<cudaStream_t>(cuda_stream);
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_use_own_stream(DfkHandle h)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  h->stream = h->own_stream;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    h->stream = h->own_stream;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 void* dfk_get_stream(DfkHandle h) { return h ? h->stream : nullptr; }
 
 DfkStatus dfk_synchronize(DfkHandle h)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  DeviceGuard guard(h->device);
-  DFK_CUDA(h, cudaStreamSynchronize(h->stream), "stream synchronize failed");
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    DFK_CUDA(h, cudaStreamSynchronize(h->stream), "stream synchronize failed");
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 const char* dfk_last_error(DfkHandle h) { return h ? h->err.c_str() : "null handle"; }
 
 DfkStatus dfk_set_profiling(DfkHandle h, int enabled)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  h->profiling = enabled != 0;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    h->profiling = enabled != 0;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_get_profile(DfkHandle h, double* main_kernel_ms, uint64_t* main_kernel_launches,
                           uint64_t* total_kernel_launches)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  DeviceGuard guard(h->device);
-  DfkStatus st = drain_events(h);
-  if (st != DFK_OK) return st;
-  if (main_kernel_ms) *main_kernel_ms = h->ev_ms_accum;
-  if (main_kernel_launches) *main_kernel_launches = h->ev_count_accum;
-  if (total_kernel_launches) *total_kernel_launches = h->launches;
-  h->ev_ms_accum = 0.0;
-  h->ev_count_accum = 0;
-  h->launches = 0;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    DeviceGuard guard(h->device);
+    DfkStatus st = drain_events(h);
+    if (st != DFK_OK) return st;
+    if (main_kernel_ms) *main_kernel_ms = h->ev_ms_accum;
+    if (main_kernel_launches) *main_kernel_launches = h->ev_count_accum;
+    if (total_kernel_launches) *total_kernel_launches = h->launches;
+    h->ev_ms_accum = 0.0;
+    h->ev_count_accum = 0;
+    h->launches = 0;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_sfm_set_params(DfkHandle h, const DfkSfmAlignerParams* p)
 {
-  if (!h || !p) return DFK_ERR_INVALID_ARG;
-  // CHECK_EQ(threads % 32, 0), CHECK_LE(blocks, max_blocks) (cu_sfmaligner.cpp:187-203)
-  if (p->step_threads % 32 != 0 || p->eval_threads % 32 != 0)
-    return fail(h, DFK_ERR_INVALID_ARG, "threads must be a multiple of 32!");
-  if (p->step_blocks > 1024 || p->eval_blocks > 1024) return fail(h, DFK_ERR_INVALID_ARG, "blocks must be less than 1024");
-  if (p->sfmparams.valid_border < 1)
-    return fail(h, DFK_ERR_INVALID_ARG, "valid_border must be >= 1 (bilinear sampling reads ix+1, iy+1)");
-  h->params = *p;
-  return DFK_OK;
+  try {
+    if (!h || !p) return DFK_ERR_INVALID_ARG;
+    // CHECK_EQ(threads % 32, 0), CHECK_LE(blocks, max_blocks) (cu_sfmaligner.cpp:187-203)
+    if (p->step_threads % 32 != 0 || p->eval_threads % 32 != 0)
+      return fail(h, DFK_ERR_INVALID_ARG, "threads must be a multiple of 32!");
+    if (p->step_blocks > 1024 || p->eval_blocks > 1024) return fail(h, DFK_ERR_INVALID_ARG, "blocks must be less than 1024");
+    if (p->sfmparams.valid_border < 1)
+      return fail(h, DFK_ERR_INVALID_ARG, "valid_border must be >= 1 (bilinear sampling reads ix+1, iy+1)");
+    h->params = *p;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_sfm_get_params(DfkHandle h, DfkSfmAlignerParams* p)
 {
-  if (!h || !p) return DFK_ERR_INVALID_ARG;
-  *p = h->params;
-  return DFK_OK;
+  try {
+    if (!h || !p) return DFK_ERR_INVALID_ARG;
+    *p = h->params;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_sfm_set_gram_mode(DfkHandle h, DfkGramMode m)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (m != DFK_GRAM_AUTO && m != DFK_GRAM_FP32 && m != DFK_GRAM_TF32X3)
-    return fail(h, DFK_ERR_INVALID_ARG, "unknown gram mode");
-  h->gram_mode = m;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (m != DFK_GRAM_AUTO && m != DFK_GRAM_FP32 && m != DFK_GRAM_TF32X3)
+      return fail(h, DFK_ERR_INVALID_ARG, "unknown gram mode");
+    h->gram_mode = m;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_se3_set_huber_delta(DfkHandle h, float v)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  h->se3_huber_delta = v;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    h->se3_huber_delta = v;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_sfm_run_step_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, float* records_dev)
 {
-  return run_batch(h, items, n, code_size, records_dev);
+  try {
+    return run_batch(h, items, n, code_size, records_dev);
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_sfm_run_step_batch_host(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size,
                                       float* records_host)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!records_host || n <= 0) return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] null/empty batch");
-  DeviceGuard guard(h->device);
-  const size_t rec = (size_t)DFK_SFM_RECORD_FLOATS(code_size);
-  DFK_CUDA(h, ensure(&h->records_dev, &h->records_cap, rec * n), "[SfmAligner::RunStep] scratch allocation failed");
-  if (h->records_host_cap < rec * n) {
-    if (h->records_host) cudaFreeHost(h->records_host);
-    h->records_host = nullptr;
-    h->records_host_cap = 0;
-    DFK_CUDA(h, cudaMallocHost((void**)&h->records_host, rec * n * sizeof(float)),
-             "[SfmAligner::RunStep] pinned allocation failed");
-    h->records_host_cap = rec * n;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!records_host || n <= 0) return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] null/empty batch");
+    if (!dfk_sfm_supports_code_size(code_size))
+      return fail(h, DFK_ERR_UNSUPPORTED,
+                  "[SfmAligner::RunStep] no kernel instantiated for code size " + std::to_string(code_size));
+    DeviceGuard guard(h->device);
+    const size_t rec = (size_t)DFK_SFM_RECORD_FLOATS(code_size);
+    DFK_CUDA(h, ensure(&h->records_dev, &h->records_cap, rec * n), "[SfmAligner::RunStep] scratch allocation failed");
+    if (h->records_host_cap < rec * n) {
+      if (h->records_host) cudaFreeHost(h->records_host);
+      h->records_host = nullptr;
+      h->records_host_cap = 0;
+      DFK_CUDA(h, cudaMallocHost((void**)&h->records_host, rec * n * sizeof(float)),
+               "[SfmAligner::RunStep] pinned allocation failed");
+      h->records_host_cap = rec * n;
+    }
+    DfkStatus st = run_batch(h, items, n, code_size, h->records_dev);
+    if (st != DFK_OK) return st;
+    DFK_CUDA(h, cudaMemcpyAsync(h->records_host, h->records_dev, rec * n * sizeof(float), cudaMemcpyDeviceToHost,
+                                h->stream),
+             "[SfmAligner::RunStep] result download failed");
+    DFK_CUDA(h, cudaStreamSynchronize(h->stream), "[SfmAligner::RunStep] kernel launch failed");
+    memcpy(records_host, h->records_host, rec * n * sizeof(float));
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
   }
-  DfkStatus st = run_batch(h, items, n, code_size, h->records_dev);
-  if (st != DFK_OK) return st;
-  DFK_CUDA(h, cudaMemcpyAsync(h->records_host, h->records_dev, rec * n * sizeof(float), cudaMemcpyDeviceToHost,
-                              h->stream),
-           "[SfmAligner::RunStep] result download failed");
-  DFK_CUDA(h, cudaStreamSynchronize(h->stream), "[SfmAligner::RunStep] kernel launch failed");
-  memcpy(records_host, h->records_host, rec * n * sizeof(float));
-  return DFK_OK;
 }
 
 DfkStatus dfk_sfm_run_step(DfkHandle h, const float pose0[7], const float pose1[7], const float* /*code0*/,
@@ -629,36 +724,44 @@ DfkStatus dfk_sfm_run_step(DfkHandle h, const float pose0[7], const float pose1[
                            const DfkImage* prx0_jac, const DfkImage* grad1, float* JtJ, float* Jtr, float* residual,
                            uint64_t* inliers)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!pose0 || !pose1 || !cam || !img0 || !img1 || !dpt0 || !valid0 || !prx0_jac || !grad1 || !JtJ || !Jtr ||
-      !residual || !inliers)
-    return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] null argument");
-  DfkSfmWorkItem w{};  // no fused depth decode: code = NULL
-  memcpy(w.pose0, pose0, sizeof(w.pose0));
-  memcpy(w.pose1, pose1, sizeof(w.pose1));
-  w.cam = *cam;
-  w.img0 = *img0; w.img1 = *img1; w.dpt0 = *dpt0; w.valid0 = *valid0; w.prx0_jac = *prx0_jac; w.grad1 = *grad1;
-  const int NP = 12 + code_size;
-  const int NH = NP * (NP + 1) / 2;
-  std::vector<float> rec((size_t)DFK_SFM_RECORD_FLOATS(code_size));
-  DfkStatus st = dfk_sfm_run_step_batch_host(h, &w, 1, code_size, rec.data());
-  if (st != DFK_OK) return st;
-  memcpy(JtJ, rec.data(), sizeof(float) * NH);
-  memcpy(Jtr, rec.data() + NH, sizeof(float) * NP);
-  *residual = rec[NH + NP];
-  uint32_t bits;
-  memcpy(&bits, &rec[NH + NP + 1], 4);
-  *inliers = bits;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!pose0 || !pose1 || !cam || !img0 || !img1 || !dpt0 || !valid0 || !prx0_jac || !grad1 || !JtJ || !Jtr ||
+        !residual || !inliers)
+      return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::RunStep] null argument");
+    DfkSfmWorkItem w{};  // no fused depth decode: code = NULL
+    memcpy(w.pose0, pose0, sizeof(w.pose0));
+    memcpy(w.pose1, pose1, sizeof(w.pose1));
+    w.cam = *cam;
+    w.img0 = *img0; w.img1 = *img1; w.dpt0 = *dpt0; w.valid0 = *valid0; w.prx0_jac = *prx0_jac; w.grad1 = *grad1;
+    const int NP = 12 + code_size;
+    const int NH = NP * (NP + 1) / 2;
+    std::vector<float> rec((size_t)DFK_SFM_RECORD_FLOATS(code_size));
+    DfkStatus st = dfk_sfm_run_step_batch_host(h, &w, 1, code_size, rec.data());
+    if (st != DFK_OK) return st;
+    memcpy(JtJ, rec.data(), sizeof(float) * NH);
+    memcpy(Jtr, rec.data() + NH, sizeof(float) * NP);
+    *residual = rec[NH + NP];
+    uint32_t bits;
+    memcpy(&bits, &rec[NH + NP + 1], 4);
+    *inliers = bits;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 static DfkStatus fetch_out(DfkHandle h, int nfloats, const char* what)
 {
-  h->launches += 1;
-  DFK_CUDA(h, cudaMemcpyAsync(h->out_host, h->out_dev, sizeof(float) * nfloats, cudaMemcpyDeviceToHost, h->stream),
-           what);
-  DFK_CUDA(h, cudaStreamSynchronize(h->stream), what);
-  return DFK_OK;
+  try {
+    h->launches += 1;
+    DFK_CUDA(h, cudaMemcpyAsync(h->out_host, h->out_dev, sizeof(float) * nfloats, cudaMemcpyDeviceToHost, h->stream),
+             what);
+    DFK_CUDA(h, cudaStreamSynchronize(h->stream), what);
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_sfm_evaluate_error(DfkHandle h, const float pose0[7], const float pose1[7], const DfkCamera* cam,
@@ -666,234 +769,277 @@ DfkStatus dfk_sfm_evaluate_error(DfkHandle h, const float pose0[7], const float 
                                  const DfkImage* /*std0*/, const DfkImage* /*grad1*/, float* residual,
                                  uint64_t* inliers)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!pose0 || !pose1 || !cam || !img0 || !img1 || !dpt0 || !residual || !inliers)
-    return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::EvaluateError] null argument");
-  const uint32_t W = img0->width, H = img0->height;
-  if (W == 0 || H == 0 || !img_ok(img0, W, H, 1) || !img_ok(img1, W, H, 1) || !img_ok(dpt0, W, H, 1))
-    return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::EvaluateError] inconsistent image views");
-  DeviceGuard guard(h->device);
-  float p10[7];
-  relative_pose(pose1, pose0, p10, nullptr, nullptr);  // cu_sfmaligner.cpp:131
-  // DenseSfm_EvaluateError uses FindCorrespondence defaults: border 1, min_dpt 0 (dense_sfm.h:91)
-  const PixelCam pc = make_pixel_cam(p10, cam, 1, 0.0f);
-  DFK_CUDA(h, launch_eval_error(pc, h->params.sfmparams.huber_delta, (int)W, (int)H, view_of(img0), view_of(img1),
-                                view_of(dpt0), h->simple_scratch, h->counter, h->out_dev, h->stream),
-           "[SfmAligner::EvaluateError] kernel launch failed");
-  DfkStatus st = fetch_out(h, 2, "[SfmAligner::EvaluateError] kernel launch failed");
-  if (st != DFK_OK) return st;
-  *residual = h->out_host[0];
-  uint32_t bits;
-  memcpy(&bits, &h->out_host[1], 4);
-  *inliers = bits;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!pose0 || !pose1 || !cam || !img0 || !img1 || !dpt0 || !residual || !inliers)
+      return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::EvaluateError] null argument");
+    const uint32_t W = img0->width, H = img0->height;
+    if (W == 0 || H == 0 || !img_ok(img0, W, H, 1) || !img_ok(img1, W, H, 1) || !img_ok(dpt0, W, H, 1))
+      return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::EvaluateError] inconsistent image views");
+    if (!cam_ok(cam, W, H)) return fail(h, DFK_ERR_INVALID_ARG, "[SfmAligner::EvaluateError] camera viewport larger than the image views");
+    DeviceGuard guard(h->device);
+    float p10[7];
+    relative_pose(pose1, pose0, p10, nullptr, nullptr);  // cu_sfmaligner.cpp:131
+    // DenseSfm_EvaluateError uses FindCorrespondence defaults: border 1, min_dpt 0 (dense_sfm.h:91)
+    const PixelCam pc = make_pixel_cam(p10, cam, 1, 0.0f);
+    DFK_CUDA(h, launch_eval_error(pc, h->params.sfmparams.huber_delta, (int)W, (int)H, view_of(img0), view_of(img1),
+                                  view_of(dpt0), h->simple_scratch, h->counter, h->out_dev, h->stream),
+             "[SfmAligner::EvaluateError] kernel launch failed");
+    DfkStatus st = fetch_out(h, 2, "[SfmAligner::EvaluateError] kernel launch failed");
+    if (st != DFK_OK) return st;
+    *residual = h->out_host[0];
+    uint32_t bits;
+    memcpy(&bits, &h->out_host[1], 4);
+    *inliers = bits;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_se3_run_step(DfkHandle h, const float se3[7], const DfkCamera* cam, const DfkImage* img0,
                            const DfkImage* img1, const DfkImage* dpt0, const DfkImage* grad1, float* JtJ, float* Jtr,
                            float* residual, uint64_t* inliers)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!se3 || !cam || !img0 || !img1 || !dpt0 || !grad1 || !JtJ || !Jtr || !residual || !inliers)
-    return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::RunStep] null argument");
-  const uint32_t W = img0->width, H = img0->height;
-  if (W == 0 || H == 0 || !img_ok(img0, W, H, 1) || !img_ok(img1, W, H, 1) || !img_ok(dpt0, W, H, 1) ||
-      !img_ok(grad1, W, H, 2))
-    return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::RunStep] inconsistent image views");
-  DeviceGuard guard(h->device);
-  const PixelCam pc = make_pixel_cam(se3, cam, 1, 0.0f);  // lucas_kanade_se3.h:52 defaults
-  const View g = view_of(grad1);
-  const bool galigned = aligned(g.ptr, 8) && g.pitch % 2 == 0;
-  DFK_CUDA(h, launch_se3_step(pc, h->se3_huber_delta, (int)W, (int)H, view_of(img0), view_of(img1), view_of(dpt0), g,
-                              galigned, h->simple_scratch, h->counter, h->out_dev, h->stream),
-           "[SE3Aligner::RunStep] Kernel launch failed");
-  DfkStatus st = fetch_out(h, 29, "[SE3Aligner::RunStep] Kernel launch failed");
-  if (st != DFK_OK) return st;
-  memcpy(JtJ, h->out_host, sizeof(float) * 21);
-  memcpy(Jtr, h->out_host + 21, sizeof(float) * 6);
-  *residual = h->out_host[27];
-  uint32_t bits;
-  memcpy(&bits, &h->out_host[28], 4);
-  *inliers = bits;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!se3 || !cam || !img0 || !img1 || !dpt0 || !grad1 || !JtJ || !Jtr || !residual || !inliers)
+      return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::RunStep] null argument");
+    const uint32_t W = img0->width, H = img0->height;
+    if (W == 0 || H == 0 || !img_ok(img0, W, H, 1) || !img_ok(img1, W, H, 1) || !img_ok(dpt0, W, H, 1) ||
+        !img_ok(grad1, W, H, 2))
+      return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::RunStep] inconsistent image views");
+    if (!cam_ok(cam, W, H)) return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::RunStep] camera viewport larger than the image views");
+    DeviceGuard guard(h->device);
+    const PixelCam pc = make_pixel_cam(se3, cam, 1, 0.0f);  // lucas_kanade_se3.h:52 defaults
+    const View g = view_of(grad1);
+    const bool galigned = aligned(g.ptr, 8) && g.pitch % 2 == 0;
+    DFK_CUDA(h, launch_se3_step(pc, h->se3_huber_delta, (int)W, (int)H, view_of(img0), view_of(img1), view_of(dpt0), g,
+                                galigned, h->simple_scratch, h->counter, h->out_dev, h->stream),
+             "[SE3Aligner::RunStep] Kernel launch failed");
+    DfkStatus st = fetch_out(h, 29, "[SE3Aligner::RunStep] Kernel launch failed");
+    if (st != DFK_OK) return st;
+    memcpy(JtJ, h->out_host, sizeof(float) * 21);
+    memcpy(Jtr, h->out_host + 21, sizeof(float) * 6);
+    *residual = h->out_host[27];
+    uint32_t bits;
+    memcpy(&bits, &h->out_host[28], 4);
+    *inliers = bits;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_se3_track(DfkHandle h, float pose_ck[7], const DfkTrackLevel* levels, int num_levels,
                         float* inlier_fraction, float* error, float* last_system, float* history, int history_capacity)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!pose_ck || !levels || num_levels <= 0)
-    return fail(h, DFK_ERR_INVALID_ARG, "[CameraTracker::TrackFrame] null argument / no pyramid levels");
-  int total_iters = 0;
-  for (int l = 0; l < num_levels; ++l) {
-    const DfkTrackLevel& L = levels[l];
-    const uint32_t W = L.img0.width, H = L.img0.height;
-    if (L.iterations < 0 || W == 0 || H == 0 || !img_ok(&L.img0, W, H, 1) || !img_ok(&L.img1, W, H, 1) ||
-        !img_ok(&L.dpt0, W, H, 1) || !img_ok(&L.grad1, W, H, 2))
-      return fail(h, DFK_ERR_INVALID_ARG,
-                  "[CameraTracker::TrackFrame] inconsistent image views / negative iteration count at level " +
-                      std::to_string(l));
-    total_iters += L.iterations;
-  }
-  if (history && history_capacity < total_iters)
-    return fail(h, DFK_ERR_INVALID_ARG, "[CameraTracker::TrackFrame] history buffer too small");
-  DeviceGuard guard(h->device);
-  const size_t nfloat = 8 + 36 * (size_t)std::max(total_iters, 1);
-  DFK_CUDA(h, ensure(&h->track_dev, &h->track_cap, nfloat), "[CameraTracker::TrackFrame] scratch allocation failed");
-  if (h->track_host_cap < nfloat + 32) {
-    if (h->track_host) cudaFreeHost(h->track_host);
-    h->track_host = nullptr;
-    h->track_host_cap = 0;
-    DFK_CUDA(h, cudaMallocHost((void**)&h->track_host, sizeof(float) * (nfloat + 32)),
-             "[CameraTracker::TrackFrame] pinned allocation failed");
-    h->track_host_cap = nfloat + 32;
-  }
-  // the pose goes to the device once; every iteration reads it there and its last block writes the update
-  memcpy(h->track_host, pose_ck, sizeof(float) * 7);
-  DFK_CUDA(h, cudaMemcpyAsync(h->track_dev, h->track_host, sizeof(float) * 7, cudaMemcpyHostToDevice, h->stream),
-           "[CameraTracker::TrackFrame] pose upload failed");
-  DFK_CUDA(h, cudaMemsetAsync(h->out_dev, 0, sizeof(float) * 32, h->stream), "[CameraTracker::TrackFrame] memset failed");
-  int it = 0;
-  uint32_t last_area = 0;
-  for (int l = num_levels - 1; l >= 0; --l) {  // coarse to fine (camera_tracker.cpp:48)
-    const DfkTrackLevel& L = levels[l];
-    const PixelCam pc = make_pixel_cam(pose_ck, &L.cam, 1, 0.0f);  // q/t are overridden by the device pose
-    const View g = view_of(&L.grad1);
-    const bool galigned = aligned(g.ptr, 8) && g.pitch % 2 == 0;
-    for (int k = 0; k < L.iterations; ++k, ++it) {
-      DFK_CUDA(h, launch_se3_step(pc, h->se3_huber_delta, (int)L.img0.width, (int)L.img0.height, view_of(&L.img0),
-                                  view_of(&L.img1), view_of(&L.dpt0), g, galigned, h->simple_scratch, h->counter,
-                                  h->out_dev, h->stream, h->track_dev, h->track_dev + 8 + 36 * (size_t)it),
-               "[CameraTracker::TrackFrame] kernel launch failed");
-      h->launches += 1;
-      last_area = L.img0.width * L.img0.height;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!pose_ck || !levels || num_levels <= 0)
+      return fail(h, DFK_ERR_INVALID_ARG, "[CameraTracker::TrackFrame] null argument / no pyramid levels");
+    int total_iters = 0;
+    for (int l = 0; l < num_levels; ++l) {
+      const DfkTrackLevel& L = levels[l];
+      const uint32_t W = L.img0.width, H = L.img0.height;
+      if (L.iterations < 0 || W == 0 || H == 0 || !img_ok(&L.img0, W, H, 1) || !img_ok(&L.img1, W, H, 1) ||
+          !img_ok(&L.dpt0, W, H, 1) || !img_ok(&L.grad1, W, H, 2) || !cam_ok(&L.cam, W, H))
+        return fail(h, DFK_ERR_INVALID_ARG,
+                    "[CameraTracker::TrackFrame] inconsistent image views / camera larger than them / negative iteration count at level " +
+                        std::to_string(l));
+      total_iters += L.iterations;
     }
+    if (history && history_capacity < total_iters)
+      return fail(h, DFK_ERR_INVALID_ARG, "[CameraTracker::TrackFrame] history buffer too small");
+    DeviceGuard guard(h->device);
+    const size_t nfloat = 8 + 36 * (size_t)std::max(total_iters, 1);
+    DFK_CUDA(h, ensure(&h->track_dev, &h->track_cap, nfloat), "[CameraTracker::TrackFrame] scratch allocation failed");
+    if (h->track_host_cap < nfloat + 32) {
+      if (h->track_host) cudaFreeHost(h->track_host);
+      h->track_host = nullptr;
+      h->track_host_cap = 0;
+      DFK_CUDA(h, cudaMallocHost((void**)&h->track_host, sizeof(float) * (nfloat + 32)),
+               "[CameraTracker::TrackFrame] pinned allocation failed");
+      h->track_host_cap = nfloat + 32;
+    }
+    // the pose goes to the device once; every iteration reads it there and its last block writes the update
+    memcpy(h->track_host, pose_ck, sizeof(float) * 7);
+    DFK_CUDA(h, cudaMemcpyAsync(h->track_dev, h->track_host, sizeof(float) * 7, cudaMemcpyHostToDevice, h->stream),
+             "[CameraTracker::TrackFrame] pose upload failed");
+    DFK_CUDA(h, cudaMemsetAsync(h->out_dev, 0, sizeof(float) * 32, h->stream), "[CameraTracker::TrackFrame] memset failed");
+    int it = 0;
+    uint32_t last_area = 0;
+    for (int l = num_levels - 1; l >= 0; --l) {  // coarse to fine (camera_tracker.cpp:48)
+      const DfkTrackLevel& L = levels[l];
+      const PixelCam pc = make_pixel_cam(pose_ck, &L.cam, 1, 0.0f);  // q/t are overridden by the device pose
+      const View g = view_of(&L.grad1);
+      const bool galigned = aligned(g.ptr, 8) && g.pitch % 2 == 0;
+      for (int k = 0; k < L.iterations; ++k, ++it) {
+        DFK_CUDA(h, launch_se3_step(pc, h->se3_huber_delta, (int)L.img0.width, (int)L.img0.height, view_of(&L.img0),
+                                    view_of(&L.img1), view_of(&L.dpt0), g, galigned, h->simple_scratch, h->counter,
+                                    h->out_dev, h->stream, h->track_dev, h->track_dev + 8 + 36 * (size_t)it),
+                 "[CameraTracker::TrackFrame] kernel launch failed");
+        h->launches += 1;
+        last_area = L.img0.width * L.img0.height;
+      }
+    }
+    // one read-back: final pose, the last evaluated system, the per-iteration history
+    float* host_sys = h->track_host + nfloat;
+    DFK_CUDA(h, cudaMemcpyAsync(h->track_host, h->track_dev, sizeof(float) * (8 + 36 * (size_t)total_iters),
+                                cudaMemcpyDeviceToHost, h->stream),
+             "[CameraTracker::TrackFrame] read-back failed");
+    DFK_CUDA(h, cudaMemcpyAsync(host_sys, h->out_dev, sizeof(float) * 29, cudaMemcpyDeviceToHost, h->stream),
+             "[CameraTracker::TrackFrame] read-back failed");
+    DFK_CUDA(h, cudaStreamSynchronize(h->stream), "[CameraTracker::TrackFrame] stream synchronize failed");
+    memcpy(pose_ck, h->track_host, sizeof(float) * 7);
+    uint32_t inl = 0;
+    memcpy(&inl, &host_sys[28], 4);
+    // camera_tracker.cpp:65-69: inliers_ / error_ are recorded at the LAST ITERATION OF LEVEL 0 only; with no level-0
+    // iteration the reference keeps its previous values, so the outputs are left untouched then.  (Levels run coarse to
+    // fine, so the last evaluated system is level 0's last iteration whenever level 0 iterates at all.)
+    if (levels[0].iterations > 0) {
+      if (inlier_fraction) *inlier_fraction = last_area ? (float)inl / (float)last_area : 0.0f;
+      if (error) *error = inl != 0 ? host_sys[27] / (float)inl : INFINITY;
+    }
+    if (last_system) memcpy(last_system, host_sys, sizeof(float) * 29);
+    if (history) memcpy(history, h->track_host + 8, sizeof(float) * 36 * (size_t)total_iters);
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
   }
-  // one read-back: final pose, the last evaluated system, the per-iteration history
-  float* host_sys = h->track_host + nfloat;
-  DFK_CUDA(h, cudaMemcpyAsync(h->track_host, h->track_dev, sizeof(float) * (8 + 36 * (size_t)total_iters),
-                              cudaMemcpyDeviceToHost, h->stream),
-           "[CameraTracker::TrackFrame] read-back failed");
-  DFK_CUDA(h, cudaMemcpyAsync(host_sys, h->out_dev, sizeof(float) * 29, cudaMemcpyDeviceToHost, h->stream),
-           "[CameraTracker::TrackFrame] read-back failed");
-  DFK_CUDA(h, cudaStreamSynchronize(h->stream), "[CameraTracker::TrackFrame] stream synchronize failed");
-  memcpy(pose_ck, h->track_host, sizeof(float) * 7);
-  uint32_t inl = 0;
-  memcpy(&inl, &host_sys[28], 4);
-  // camera_tracker.cpp:65-69: statistics of the last evaluated system (the reference records them at level 0)
-  if (inlier_fraction) *inlier_fraction = last_area ? (float)inl / (float)last_area : 0.0f;
-  if (error) *error = inl != 0 ? host_sys[27] / (float)inl : INFINITY;
-  if (last_system) memcpy(last_system, host_sys, sizeof(float) * 29);
-  if (history) memcpy(history, h->track_host + 8, sizeof(float) * 36 * (size_t)total_iters);
-  return DFK_OK;
 }
 
 DfkStatus dfk_se3_warp(DfkHandle h, const float se3[7], const DfkCamera* cam, const DfkImage* img0,
                        const DfkImage* img1, const DfkImage* dpt0, const DfkImage* img2, float* residual,
                        uint64_t* inliers)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!se3 || !cam || !img0 || !img1 || !dpt0 || !img2 || !residual || !inliers)
-    return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::Warp] null argument");
-  const uint32_t W = img0->width, H = img0->height;
-  if (W == 0 || H == 0 || !img_ok(img0, W, H, 1) || !img_ok(img1, W, H, 1) || !img_ok(dpt0, W, H, 1) ||
-      !img_ok(img2, W, H, 1))
-    return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::Warp] inconsistent image views");
-  DeviceGuard guard(h->device);
-  // depth <= 0 -> skip ; PixelValid(pix1, 1) (cu_se3aligner.cpp:89-97)
-  const PixelCam pc = make_pixel_cam(se3, cam, 1, 0.0f);
-  DFK_CUDA(h, launch_warp(pc, (int)W, (int)H, view_of(img0), view_of(img1), view_of(dpt0), (float*)img2->ptr,
-                          (uint32_t)(img2->pitch_bytes / 4), h->simple_scratch, h->counter, h->out_dev, h->stream),
-           "[SE3Aligner::Warp] Kernel launch failed (kernel_warp_calculate)");
-  DfkStatus st = fetch_out(h, 2, "[SE3Aligner::Warp] Kernel launch failed (kernel_finalize_reduction)");
-  if (st != DFK_OK) return st;
-  *residual = h->out_host[0];
-  uint32_t bits;
-  memcpy(&bits, &h->out_host[1], 4);
-  *inliers = bits;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!se3 || !cam || !img0 || !img1 || !dpt0 || !img2 || !residual || !inliers)
+      return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::Warp] null argument");
+    const uint32_t W = img0->width, H = img0->height;
+    if (W == 0 || H == 0 || !img_ok(img0, W, H, 1) || !img_ok(img1, W, H, 1) || !img_ok(dpt0, W, H, 1) ||
+        !img_ok(img2, W, H, 1))
+      return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::Warp] inconsistent image views");
+    if (!cam_ok(cam, W, H)) return fail(h, DFK_ERR_INVALID_ARG, "[SE3Aligner::Warp] camera viewport larger than the image views");
+    DeviceGuard guard(h->device);
+    // depth <= 0 -> skip ; PixelValid(pix1, 1) (cu_se3aligner.cpp:89-97)
+    const PixelCam pc = make_pixel_cam(se3, cam, 1, 0.0f);
+    DFK_CUDA(h, launch_warp(pc, (int)W, (int)H, view_of(img0), view_of(img1), view_of(dpt0), (float*)img2->ptr,
+                            (uint32_t)(img2->pitch_bytes / 4), h->simple_scratch, h->counter, h->out_dev, h->stream),
+             "[SE3Aligner::Warp] Kernel launch failed (kernel_warp_calculate)");
+    DfkStatus st = fetch_out(h, 2, "[SE3Aligner::Warp] Kernel launch failed (kernel_finalize_reduction)");
+    if (st != DFK_OK) return st;
+    *residual = h->out_host[0];
+    uint32_t bits;
+    memcpy(&bits, &h->out_host[1], 4);
+    *inliers = bits;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_update_depth(DfkHandle h, const float* code, int code_size, const DfkImage* prx_orig,
                            const DfkImage* prx_jac, float avg_dpt, const DfkImage* dpt_out)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!code || !prx_orig || !prx_jac || !dpt_out) return fail(h, DFK_ERR_INVALID_ARG, "[UpdateDepth] null argument");
-  if (code_size < 1 || code_size > 256) return fail(h, DFK_ERR_UNSUPPORTED, "[UpdateDepth] code size out of range");
-  const uint32_t W = dpt_out->width, H = dpt_out->height;
-  if (W == 0 || H == 0 || !img_ok(prx_orig, W, H, 1) || !img_ok(prx_jac, W, H, code_size) || !img_ok(dpt_out, W, H, 1))
-    return fail(h, DFK_ERR_INVALID_ARG, "[UpdateDepth] inconsistent image views");
-  DeviceGuard guard(h->device);
-  DFK_CUDA(h, cudaMemcpyAsync(h->code_dev, code, sizeof(float) * code_size, cudaMemcpyHostToDevice, h->stream),
-           "[UpdateDepth] code upload failed");
-  DFK_CUDA(h, launch_update_depth(h->code_dev, code_size, (int)W, (int)H, view_of(prx_orig), view_of(prx_jac),
-                                  avg_dpt, (float*)dpt_out->ptr, (uint32_t)(dpt_out->pitch_bytes / 4), h->stream),
-           "[UpdateDepth] kernel launch failed");
-  h->launches += 1;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!code || !prx_orig || !prx_jac || !dpt_out) return fail(h, DFK_ERR_INVALID_ARG, "[UpdateDepth] null argument");
+    if (code_size < 1 || code_size > 256) return fail(h, DFK_ERR_UNSUPPORTED, "[UpdateDepth] code size out of range");
+    const uint32_t W = dpt_out->width, H = dpt_out->height;
+    if (W == 0 || H == 0 || !img_ok(prx_orig, W, H, 1) || !img_ok(prx_jac, W, H, code_size) || !img_ok(dpt_out, W, H, 1))
+      return fail(h, DFK_ERR_INVALID_ARG, "[UpdateDepth] inconsistent image views");
+    DeviceGuard guard(h->device);
+    DFK_CUDA(h, cudaMemcpyAsync(h->code_dev, code, sizeof(float) * code_size, cudaMemcpyHostToDevice, h->stream),
+             "[UpdateDepth] code upload failed");
+    DFK_CUDA(h, launch_update_depth(h->code_dev, code_size, (int)W, (int)H, view_of(prx_orig), view_of(prx_jac),
+                                    avg_dpt, (float*)dpt_out->ptr, (uint32_t)(dpt_out->pitch_bytes / 4), h->stream),
+             "[UpdateDepth] kernel launch failed");
+    h->launches += 1;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_sobel_gradients(DfkHandle h, const DfkImage* img, const DfkImage* grad)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!img || !grad) return fail(h, DFK_ERR_INVALID_ARG, "[SobelGradients] null argument");
-  const uint32_t W = img->width, H = img->height;
-  if (W == 0 || H == 0 || !img_ok(img, W, H, 1) || !img_ok(grad, W, H, 2))
-    return fail(h, DFK_ERR_INVALID_ARG, "[SobelGradients] inconsistent image views");
-  DeviceGuard guard(h->device);
-  DFK_CUDA(h, launch_sobel((int)W, (int)H, view_of(img), (float*)grad->ptr, (uint32_t)(grad->pitch_bytes / 4),
-                           h->stream),
-           "Kernel launch failed (kernel_sobel_gradients)");
-  h->launches += 1;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!img || !grad) return fail(h, DFK_ERR_INVALID_ARG, "[SobelGradients] null argument");
+    const uint32_t W = img->width, H = img->height;
+    if (W == 0 || H == 0 || !img_ok(img, W, H, 1) || !img_ok(grad, W, H, 2))
+      return fail(h, DFK_ERR_INVALID_ARG, "[SobelGradients] inconsistent image views");
+    DeviceGuard guard(h->device);
+    DFK_CUDA(h, launch_sobel((int)W, (int)H, view_of(img), (float*)grad->ptr, (uint32_t)(grad->pitch_bytes / 4),
+                             h->stream),
+             "Kernel launch failed (kernel_sobel_gradients)");
+    h->launches += 1;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_gaussian_blur_down(DfkHandle h, const DfkImage* in, const DfkImage* out)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!in || !out) return fail(h, DFK_ERR_INVALID_ARG, "[GaussianBlurDown] null argument");
-  if (in->width == 0 || in->height == 0 || out->width == 0 || out->height == 0 ||
-      !img_ok(in, in->width, in->height, 1) || !img_ok(out, out->width, out->height, 1))
-    return fail(h, DFK_ERR_INVALID_ARG, "[GaussianBlurDown] inconsistent image views");
-  DeviceGuard guard(h->device);
-  DFK_CUDA(h, launch_blur_down((int)in->width, (int)in->height, view_of(in), (int)out->width, (int)out->height,
-                               (float*)out->ptr, (uint32_t)(out->pitch_bytes / 4), h->stream),
-           "Kernel launch failed (kernel_gaussian_blur_down)");
-  h->launches += 1;
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!in || !out) return fail(h, DFK_ERR_INVALID_ARG, "[GaussianBlurDown] null argument");
+    if (in->width == 0 || in->height == 0 || out->width == 0 || out->height == 0 ||
+        !img_ok(in, in->width, in->height, 1) || !img_ok(out, out->width, out->height, 1))
+      return fail(h, DFK_ERR_INVALID_ARG, "[GaussianBlurDown] inconsistent image views");
+    DeviceGuard guard(h->device);
+    DFK_CUDA(h, launch_blur_down((int)in->width, (int)in->height, view_of(in), (int)out->width, (int)out->height,
+                                 (float*)out->ptr, (uint32_t)(out->pitch_bytes / 4), h->stream),
+             "Kernel launch failed (kernel_gaussian_blur_down)");
+    h->launches += 1;
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_build_image_pyramid(DfkHandle h, const DfkImage* imgs, const DfkImage* grads, int levels)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!imgs || levels <= 0) return fail(h, DFK_ERR_INVALID_ARG, "[BuildImagePyramid] null argument / no levels");
-  for (int l = 1; l < levels; ++l) {
-    DfkStatus st = dfk_gaussian_blur_down(h, &imgs[l - 1], &imgs[l]);
-    if (st != DFK_OK) return st;
-  }
-  if (grads)
-    for (int l = 0; l < levels; ++l) {
-      DfkStatus st = dfk_sobel_gradients(h, &imgs[l], &grads[l]);
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!imgs || levels <= 0) return fail(h, DFK_ERR_INVALID_ARG, "[BuildImagePyramid] null argument / no levels");
+    for (int l = 1; l < levels; ++l) {
+      DfkStatus st = dfk_gaussian_blur_down(h, &imgs[l - 1], &imgs[l]);
       if (st != DFK_OK) return st;
     }
-  return DFK_OK;
+    if (grads)
+      for (int l = 0; l < levels; ++l) {
+        DfkStatus st = dfk_sobel_gradients(h, &imgs[l], &grads[l]);
+        if (st != DFK_OK) return st;
+      }
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 DfkStatus dfk_squared_error(DfkHandle h, const DfkImage* a, const DfkImage* b, float* out)
 {
-  if (!h) return DFK_ERR_INVALID_ARG;
-  if (!a || !b || !out) return fail(h, DFK_ERR_INVALID_ARG, "[SquaredError] null argument");
-  const uint32_t W = a->width, H = a->height;
-  if (W == 0 || H == 0 || !img_ok(a, W, H, 1) || !img_ok(b, W, H, 1))
-    return fail(h, DFK_ERR_INVALID_ARG, "[SquaredError] inconsistent image views");
-  DeviceGuard guard(h->device);
-  DFK_CUDA(h, launch_squared_error((int)W, (int)H, view_of(a), view_of(b), h->simple_scratch, h->counter, h->out_dev,
-                                   h->stream),
-           "[SquaredError] kernel launch failed");
-  DfkStatus st = fetch_out(h, 1, "[SquaredError] kernel launch failed");
-  if (st != DFK_OK) return st;
-  *out = h->out_host[0];
-  return DFK_OK;
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!a || !b || !out) return fail(h, DFK_ERR_INVALID_ARG, "[SquaredError] null argument");
+    const uint32_t W = a->width, H = a->height;
+    if (W == 0 || H == 0 || !img_ok(a, W, H, 1) || !img_ok(b, W, H, 1))
+      return fail(h, DFK_ERR_INVALID_ARG, "[SquaredError] inconsistent image views");
+    DeviceGuard guard(h->device);
+    DFK_CUDA(h, launch_squared_error((int)W, (int)H, view_of(a), view_of(b), h->simple_scratch, h->counter, h->out_dev,
+                                     h->stream),
+             "[SquaredError] kernel launch failed");
+    DfkStatus st = fetch_out(h, 1, "[SquaredError] kernel launch failed");
+    if (st != DFK_OK) return st;
+    *out = h->out_host[0];
+    return DFK_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
 }
 
 }  // extern "C"

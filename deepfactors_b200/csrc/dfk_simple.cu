@@ -100,8 +100,48 @@ __device__ __forceinline__ bool reduce_finalize(float (&v)[NV], unsigned int cnt
 
 // ------------------------------------------------------------------------------ on-device Gauss-Newton update
 // camera_tracker.cpp:59-63: update = -JtJ.ldlt().solve(Jtr); translation += update.head<3>();
-// so3 = SO3::exp(update.tail<3>()) * so3.  6x6 LDL^T without pivoting (the matrix is a sum of outer products);
-// returns false (pose untouched) when a pivot is not positive, e.g. zero inliers.
+// so3 = SO3::exp(update.tail<3>()) * so3.  Eigen's LDLT is a robust Cholesky with symmetric (diagonal) pivoting that
+// still returns a solution for semi-definite / ill-conditioned systems: pivots not larger than the smallest normal
+// float contribute nothing (Eigen's LDLT::solve zeroes those components).  Same here, so a rank-deficient level moves
+// the pose where the reference moves it, and an all-zero system (no inliers) leaves it alone.
+__device__ inline void ldlt6_solve(float A[6][6] /* full symmetric, destroyed */, const float b[6], float x[6])
+{
+  int perm[6];
+  for (int i = 0; i < 6; ++i) perm[i] = i;
+  for (int k = 0; k < 6; ++k) {
+    int p = k;
+    float best = fabsf(A[k][k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (fabsf(A[i][i]) > best) {
+        best = fabsf(A[i][i]);
+        p = i;
+      }
+    if (p != k) {  // P A P^T: rows k <-> p (the finished L columns and the trailing block), then columns k <-> p
+      for (int c = 0; c < 6; ++c) { const float t = A[k][c]; A[k][c] = A[p][c]; A[p][c] = t; }
+      for (int r = 0; r < 6; ++r) { const float t = A[r][k]; A[r][k] = A[r][p]; A[r][p] = t; }
+      const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+    }
+    const float d = A[k][k];
+    if (fabsf(d) > 1.17549435e-38f) {
+      float col[6];
+      for (int i = k + 1; i < 6; ++i) col[i] = A[i][k] / d;  // L_ik
+      for (int i = k + 1; i < 6; ++i)
+        for (int j = k + 1; j < 6; ++j) A[i][j] -= col[i] * A[j][k];  // A[j][k] still holds L_jk * d
+      for (int i = k + 1; i < 6; ++i) A[i][k] = col[i];
+    } else {
+      for (int i = k + 1; i < 6; ++i) A[i][k] = 0.0f;
+    }
+  }
+  float y[6];
+  for (int i = 0; i < 6; ++i) y[i] = b[perm[i]];
+  for (int i = 0; i < 6; ++i)
+    for (int k = 0; k < i; ++k) y[i] -= A[i][k] * y[k];
+  for (int i = 0; i < 6; ++i) y[i] = fabsf(A[i][i]) > 1.17549435e-38f ? y[i] / A[i][i] : 0.0f;
+  for (int i = 5; i >= 0; --i)
+    for (int k = i + 1; k < 6; ++k) y[i] -= A[k][i] * y[k];
+  for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+}
+
 __device__ inline bool gn_update_pose(const float* __restrict__ sys /*21 JtJ packed upper, 6 Jtr*/, float* pose /*qx qy qz qw tx ty tz*/)
 {
   float A[6][6], b[6];
@@ -113,30 +153,8 @@ __device__ inline bool gn_update_pose(const float* __restrict__ sys /*21 JtJ pac
       ++h;
     }
   for (int r = 0; r < 6; ++r) b[r] = -sys[21 + r];
-  float L[6][6], D[6];
-  for (int j = 0; j < 6; ++j) {
-    float d = A[j][j];
-    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
-    if (!(d > 0.0f)) return false;
-    D[j] = d;
-    for (int i = j + 1; i < 6; ++i) {
-      float v = A[i][j];
-      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * D[k];
-      L[i][j] = v / d;
-    }
-  }
   float x[6];
-  for (int i = 0; i < 6; ++i) {  // L y = b
-    float v = b[i];
-    for (int k = 0; k < i; ++k) v -= L[i][k] * x[k];
-    x[i] = v;
-  }
-  for (int i = 0; i < 6; ++i) x[i] /= D[i];
-  for (int i = 5; i >= 0; --i) {  // L^T x = y
-    float v = x[i];
-    for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k];
-    x[i] = v;
-  }
+  ldlt6_solve(A, b, x);
   // Sophus SO3::exp (quaternion form) and left multiplication, then renormalisation
   const float th2 = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
   const float th = sqrtf(th2);

@@ -91,6 +91,11 @@ inline HandlePtr MakeHandle()
   DfkHandle h = nullptr;
   DfkStatus st = dfk_create(-1, &h);
   if (st != DFK_OK) throw CUDAException(st, "dfk_create failed: " + std::string(dfk_status_string(st)));
+  // Ordering contract of the drop-in facade = the reference's: every launch goes to the LEGACY DEFAULT stream
+  // (cu_sfmaligner.cpp:175-179 launches without a stream argument), so inputs an integrator produced asynchronously on
+  // stream 0 (uploads, pyramid / network kernels) are complete before an aligner reads them.  A handle's own stream is
+  // non-blocking and NOT ordered against stream 0; callers that want it (or their own stream) say so with SetStream.
+  dfk_set_stream(h, nullptr);
   return HandlePtr(h);
 }
 }  // namespace detail
@@ -290,6 +295,10 @@ public:
   }
 
   DfkHandle handle() const { return h_.get(); }  // extension: batched / asynchronous entry points of dfk.h
+  // extension: launch on `stream` (a cudaStream_t; nullptr = the legacy default stream, the facade's default) or on the
+  // handle's private non-blocking stream.  The caller then owns the ordering against its producers.
+  void SetStream(void* stream) { detail::Check(h_.get(), dfk_set_stream(h_.get(), stream)); }
+  void UseOwnStream() { detail::Check(h_.get(), dfk_use_own_stream(h_.get())); }
 
 private:
   void Upload() { Upload(params_); }
@@ -357,6 +366,9 @@ public:
     return r;
   }
 
+  DfkHandle handle() const { return h_.get(); }
+  void SetStream(void* stream) { detail::Check(h_.get(), dfk_set_stream(h_.get(), stream)); }  // see SfmAligner::SetStream
+  void UseOwnStream() { detail::Check(h_.get(), dfk_use_own_stream(h_.get())); }
   void SetHuberDelta(float val)
   {
     huber_delta_ = val;

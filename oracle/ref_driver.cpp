@@ -1,0 +1,269 @@
+// oracle/ref_driver.cpp -- builds oracle/_ref/libdfk_ref.so: the REFERENCE's own per-pixel headers
+//   /root/reference/sources/common/algorithm/{dense_sfm,warping,pinhole_camera(_impl),lucas_kanade_se3,m_estimators}.h
+//   /root/reference/sources/cuda/{reduction_items,kernel_utils}.h
+// compiled unmodified from where they lie (no reference source is copied into this repository), against the stand-in
+// third-party headers under oracle/shim/ (Eigen, Sophus, VisionCore and OpenCV are not installed in this image), and
+// driven by the host loop of the reference's own GPU-vs-CPU test (tests/ut_sfmaligner.cpp:297-315).
+//
+// TEST INFRASTRUCTURE ONLY: tests/test_oracle_ref.py checks the hand-written oracle (oracle/dfk_oracle_impl.inc) against
+// this library; bench.py may time it as the CPU baseline ("kind": "reference").  Nothing in the product links it.
+// What this pins: every line of the reference's own math (DenseSfm, DenseSfm_EvaluateError, LucasKanadeSE3,
+// FindCorrespondence + Jacobians, RelativePose + Jacobians, PinholeCamera, HuberWeight, DepthFromCode).  What it cannot
+// pin: the conventions restated in oracle/shim/ (getBilinear, quaternion rotate, SO3 product) -- see the shim headers.
+//
+// The C entry points mirror oracle/dfk_oracle.h (pitches in ELEMENTS of float) so the test can call both alike.
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#include <Eigen/Core>
+#include <sophus/se3.hpp>
+#include <VisionCore/Buffers/Image2D.hpp>
+
+#include "dense_sfm.h"
+#include "lucas_kanade_se3.h"
+#include "warping.h"
+
+namespace {
+
+using Grad = Eigen::Matrix<float, 1, 2>;
+using ImgView = vc::Image2DView<float, vc::TargetHost>;
+using GradView = vc::Image2DView<Grad, vc::TargetHost>;
+
+template <typename T>
+Sophus::SE3<T> make_se3(const T p[7])
+{
+  return Sophus::SE3<T>(Sophus::SO3<T>(p[0], p[1], p[2], p[3]), Eigen::Matrix<T, 3, 1>(p[4], p[5], p[6]));
+}
+
+template <typename T>
+void store_se3(const Sophus::SE3<T>& s, T p[7])
+{
+  p[0] = s.so3().x(); p[1] = s.so3().y(); p[2] = s.so3().z(); p[3] = s.so3().w();
+  p[4] = s.translation()[0]; p[5] = s.translation()[1]; p[6] = s.translation()[2];
+}
+
+ImgView view(const float* p, int w, int h, size_t pitch_floats)
+{
+  return ImgView(const_cast<float*>(p), (size_t)w, (size_t)h, pitch_floats * sizeof(float));
+}
+
+struct Cam6 {
+  float fx, fy, u0, v0, width, height;
+};
+struct Params5 {
+  float huber_delta, ocl_th, avg_dpt, min_dpt;
+  int valid_border;
+};
+
+// lucas_kanade_se3.h:74 writes `ReductionItem::HessianType(J.transpose())` without `typename`: fine for nvcc's device
+// front end (the only place the reference instantiates it), ill-formed for g++ when HessianType is a type.  The item type
+// is a template parameter of LucasKanadeSE3, so the host build passes this derived item whose `HessianType` IS a
+// non-type: a static function building the very same packed matrix.  The reference header stays untouched.
+struct LkItem : df::JTJJrReductionItem<float, 6> {
+  using Base = df::JTJJrReductionItem<float, 6>;
+  static Base::HessianType HessianType(const Base::JacobianType& v) { return Base::HessianType(v); }
+};
+
+template <int CS>
+void sfm_run_step(const float* pose0, const float* pose1, const Cam6* c, int width, int height, const float* img0,
+                  size_t img0_pitch, const float* img1, size_t img1_pitch, const float* dpt0, size_t dpt0_pitch,
+                  float* valid0, size_t valid0_pitch, const float* jac, size_t jac_pitch, const float* grad1,
+                  size_t grad1_pitch, const Params5* prm, float* JtJ, float* Jtr, float* residual, uint64_t* inliers)
+{
+  using Item = df::JTJJrReductionItem<float, 12 + CS>;
+  const Sophus::SE3f p0 = make_se3(pose0), p1 = make_se3(pose1);
+  const df::PinholeCamera<float> cam(c->fx, c->fy, c->u0, c->v0, c->width, c->height);
+  df::DenseSfmParams sp;
+  sp.huber_delta = prm->huber_delta; sp.ocl_th = prm->ocl_th; sp.avg_dpt = prm->avg_dpt; sp.min_dpt = prm->min_dpt;
+  sp.valid_border = prm->valid_border;
+  // tests/ut_sfmaligner.cpp:297-300 (== cu_sfmaligner.cpp:164-166)
+  Eigen::Matrix<float, 6, 6> pose10_J_pose0;
+  Eigen::Matrix<float, 6, 6> pose10_J_pose1;
+  const Sophus::SE3f pose_10 = df::RelativePose(p1, p0, pose10_J_pose1, pose10_J_pose0);
+  Eigen::Matrix<float, CS, 1> code;
+  code.setZero();  // dead inside DenseSfm (dense_sfm.h:133-201 never reads it)
+  const ImgView vimg0 = view(img0, width, height, img0_pitch), vimg1 = view(img1, width, height, img1_pitch);
+  const ImgView vdpt0 = view(dpt0, width, height, dpt0_pitch);
+  const ImgView vstd0 = view(dpt0, width, height, dpt0_pitch);  // std0 only feeds the dead uncertainty weight (:66)
+  ImgView vvalid0 = view(valid0, width, height, valid0_pitch);
+  const ImgView vjac(const_cast<float*>(jac), (size_t)width * CS, (size_t)height, jac_pitch * sizeof(float));
+  const GradView vgrad(reinterpret_cast<Grad*>(const_cast<float*>(grad1)), (size_t)width, (size_t)height,
+                       grad1_pitch * sizeof(float));
+  Item result;
+  // tests/ut_sfmaligner.cpp:303-315: x outer, y inner
+  for (int x = 0; x < width; x += 1)
+    for (int y = 0; y < height; y += 1)
+      df::DenseSfm<float, CS, vc::TargetHost>(x, y, pose_10, pose10_J_pose0, pose10_J_pose1, code, cam, vimg0, vimg1,
+                                              vdpt0, vstd0, vvalid0, vjac, vgrad, sp, result);
+  constexpr int NP = 12 + CS;
+  for (int k = 0; k < NP * (NP + 1) / 2; ++k) JtJ[k] = result.JtJ.coeff()(k);
+  for (int k = 0; k < NP; ++k) Jtr[k] = result.Jtr(k);
+  *residual = result.residual;
+  *inliers = result.inliers;
+}
+
+template <int CS>
+void update_depth(const float* code_in, int width, int height, const float* prx_orig, size_t prx_pitch,
+                  const float* jac, size_t jac_pitch, float avg_dpt, float* dpt_out, size_t dpt_pitch)
+{
+  Eigen::Matrix<float, CS, 1> code;
+  for (int k = 0; k < CS; ++k) code(k) = code_in[k];
+  const ImgView vprx = view(prx_orig, width, height, prx_pitch);
+  const ImgView vjac(const_cast<float*>(jac), (size_t)width * CS, (size_t)height, jac_pitch * sizeof(float));
+  ImgView vout = view(dpt_out, width, height, dpt_pitch);
+  // body of kernel_update_depth (cuda/cu_image_proc.cpp:255-263), every pixel once
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x) {
+      Eigen::Map<const Eigen::Matrix<float, 1, CS>> tmp(&vjac(x * CS, y));
+      const Eigen::Matrix<float, 1, CS> prx_J_cde(tmp);
+      vout(x, y) = df::DepthFromCode(code, prx_J_cde, vprx(x, y), avg_dpt);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfkr_supports_code_size(int cs) { return cs == 8 || cs == 16 || cs == 32 || cs == 64 || cs == 128; }
+
+// warping.h:98-137; jac_a / jac_b 6x6 row-major
+void dfkr_relative_pose_f(const float a[7], const float b[7], float ab[7], float jac_a[36], float jac_b[36])
+{
+  Eigen::Matrix<float, 6, 6> ja, jb;
+  const Sophus::SE3f r = df::RelativePose(make_se3(a), make_se3(b), ja, jb);
+  store_se3(r, ab);
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      if (jac_a) jac_a[i * 6 + j] = ja(i, j);
+      if (jac_b) jac_b[i * 6 + j] = jb(i, j);
+    }
+}
+void dfkr_relative_pose_d(const double a[7], const double b[7], double ab[7], double jac_a[36], double jac_b[36])
+{
+  Eigen::Matrix<double, 6, 6> ja, jb;
+  const Sophus::SE3d r = df::RelativePose(make_se3(a), make_se3(b), ja, jb);
+  store_se3(r, ab);
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      if (jac_a) jac_a[i * 6 + j] = ja(i, j);
+      if (jac_b) jac_b[i * 6 + j] = jb(i, j);
+    }
+}
+
+// FindCorrespondence + its Jacobians for one (integer) pixel, double: out[0]=valid, out[1..2]=pix1,
+// out[3..14]=corresp_J_pose (2x6 row major), out[15..16]=pix1_J_prx   (same packing as dfko_probe_pixel_d)
+void dfkr_probe_pixel_d(size_t x, size_t y, double dpt, const Cam6* c, const double pose[7], int border, double min_dpt,
+                        double avg_dpt, double out[17])
+{
+  const df::PinholeCamera<double> cam(c->fx, c->fy, c->u0, c->v0, c->width, c->height);
+  const Sophus::SE3d se3 = make_se3(pose);
+  for (int i = 0; i < 17; ++i) out[i] = 0;
+  // check_bounds = false keeps pt / tpt filled for out-of-image pixels (the Jacobians only need tpt)
+  const df::Correspondence<double> bounded = df::FindCorrespondence(x, y, dpt, cam, se3, border, min_dpt);
+  const df::Correspondence<double> corr = df::FindCorrespondence(x, y, dpt, cam, se3, border, min_dpt, false);
+  out[0] = bounded.valid ? 1.0 : 0.0;
+  if (!corr.valid) return;
+  out[1] = corr.pix1[0];
+  out[2] = corr.pix1[1];
+  const Eigen::Matrix<double, 2, 6> A = df::FindCorrespondenceJacobianPose(corr, dpt, cam, se3);
+  for (int k = 0; k < 6; ++k) {
+    out[3 + k] = A(0, k);
+    out[9 + k] = A(1, k);
+  }
+  Eigen::Matrix<double, 2, 1> pJ;
+  df::FindCorrespondenceJacobianPrx(corr, dpt, cam, se3, avg_dpt, pJ);
+  out[15] = pJ(0);
+  out[16] = pJ(1);
+}
+
+float dfkr_huber_weight_f(float x, float delta) { return df::HuberWeight(x, delta); }
+
+// SfmAligner::RunStep's math on the host: the loop of tests/ut_sfmaligner.cpp:297-315.  Returns 0, or -1 for a code size
+// that is not instantiated here.
+int dfkr_sfm_run_step_f(const float pose0[7], const float pose1[7], int code_size, const Cam6* cam, int width,
+                        int height, const float* img0, size_t img0_pitch, const float* img1, size_t img1_pitch,
+                        const float* dpt0, size_t dpt0_pitch, float* valid0, size_t valid0_pitch,
+                        const float* prx0_jac, size_t jac_pitch, const float* grad1, size_t grad1_pitch,
+                        const Params5* params, float* JtJ, float* Jtr, float* residual, uint64_t* inliers)
+{
+#define DFKR_CASE(CS)                                                                                                  \
+  case CS:                                                                                                             \
+    sfm_run_step<CS>(pose0, pose1, cam, width, height, img0, img0_pitch, img1, img1_pitch, dpt0, dpt0_pitch, valid0,   \
+                     valid0_pitch, prx0_jac, jac_pitch, grad1, grad1_pitch, params, JtJ, Jtr, residual, inliers);      \
+    return 0;
+  switch (code_size) {
+    DFKR_CASE(8)
+    DFKR_CASE(16)
+    DFKR_CASE(32)
+    DFKR_CASE(64)
+    DFKR_CASE(128)
+    default: return -1;
+  }
+#undef DFKR_CASE
+}
+
+// SfmAligner::EvaluateError's math (cu_sfmaligner.cpp:120-147, dense_sfm.h:79-119), x outer / y inner
+void dfkr_sfm_evaluate_error_f(const float pose0[7], const float pose1[7], const Cam6* c, int width, int height,
+                               const float* img0, size_t img0_pitch, const float* img1, size_t img1_pitch,
+                               const float* dpt0, size_t dpt0_pitch, const float* grad1, size_t grad1_pitch,
+                               const Params5* prm, float* residual, uint64_t* inliers)
+{
+  const df::PinholeCamera<float> cam(c->fx, c->fy, c->u0, c->v0, c->width, c->height);
+  df::DenseSfmParams sp;
+  sp.huber_delta = prm->huber_delta; sp.ocl_th = prm->ocl_th; sp.avg_dpt = prm->avg_dpt; sp.min_dpt = prm->min_dpt;
+  sp.valid_border = prm->valid_border;
+  const Sophus::SE3f pose_10 = df::RelativePose(make_se3(pose1), make_se3(pose0));  // cu_sfmaligner.cpp:131
+  const ImgView vimg0 = view(img0, width, height, img0_pitch), vimg1 = view(img1, width, height, img1_pitch);
+  const ImgView vdpt0 = view(dpt0, width, height, dpt0_pitch);
+  const GradView vgrad(reinterpret_cast<Grad*>(const_cast<float*>(grad1)), (size_t)width, (size_t)height,
+                       grad1_pitch * sizeof(float));
+  df::CorrespondenceReductionItem<float> result;
+  for (int x = 0; x < width; ++x)
+    for (int y = 0; y < height; ++y)
+      df::DenseSfm_EvaluateError<float, 32, vc::TargetHost>(x, y, pose_10, cam, vimg0, vimg1, vdpt0, vdpt0, vgrad, sp,
+                                                            result);
+  *residual = result.residual;
+  *inliers = result.inliers;
+}
+
+// SE3Aligner::RunStep's math (cu_se3aligner.cpp:37-59, lucas_kanade_se3.h:41-77), x outer / y inner
+void dfkr_se3_run_step_f(const float se3[7], const Cam6* c, int width, int height, const float* img0, size_t img0_pitch,
+                         const float* img1, size_t img1_pitch, const float* dpt0, size_t dpt0_pitch,
+                         const float* grad1, size_t grad1_pitch, float huber_delta, float* JtJ, float* Jtr,
+                         float* residual, uint64_t* inliers)
+{
+  using Item = LkItem;
+  const df::PinholeCamera<float> cam(c->fx, c->fy, c->u0, c->v0, c->width, c->height);
+  const Sophus::SE3f pose = make_se3(se3);
+  const ImgView vimg0 = view(img0, width, height, img0_pitch), vimg1 = view(img1, width, height, img1_pitch);
+  const ImgView vdpt0 = view(dpt0, width, height, dpt0_pitch);
+  const GradView vgrad(reinterpret_cast<Grad*>(const_cast<float*>(grad1)), (size_t)width, (size_t)height,
+                       grad1_pitch * sizeof(float));
+  Item sum;
+  for (int x = 0; x < width; ++x)
+    for (int y = 0; y < height; ++y)
+      sum += df::LucasKanadeSE3<float, vc::TargetHost, Sophus::SE3f, df::PinholeCamera<float>, Item>(
+          x, y, pose, cam, vimg0, vimg1, vdpt0, vgrad, huber_delta);
+  for (int k = 0; k < 21; ++k) JtJ[k] = sum.JtJ.coeff()(k);
+  for (int k = 0; k < 6; ++k) Jtr[k] = sum.Jtr(k);
+  *residual = sum.residual;
+  *inliers = sum.inliers;
+}
+
+// UpdateDepth's math (cu_image_proc.cpp:248-264, warping.h:52-69)
+int dfkr_update_depth_f(const float* code, int code_size, int width, int height, const float* prx_orig,
+                        size_t prx_pitch, const float* prx_jac, size_t jac_pitch, float avg_dpt, float* dpt_out,
+                        size_t dpt_pitch)
+{
+  switch (code_size) {
+    case 8: update_depth<8>(code, width, height, prx_orig, prx_pitch, prx_jac, jac_pitch, avg_dpt, dpt_out, dpt_pitch); return 0;
+    case 16: update_depth<16>(code, width, height, prx_orig, prx_pitch, prx_jac, jac_pitch, avg_dpt, dpt_out, dpt_pitch); return 0;
+    case 32: update_depth<32>(code, width, height, prx_orig, prx_pitch, prx_jac, jac_pitch, avg_dpt, dpt_out, dpt_pitch); return 0;
+    case 64: update_depth<64>(code, width, height, prx_orig, prx_pitch, prx_jac, jac_pitch, avg_dpt, dpt_out, dpt_pitch); return 0;
+    case 128: update_depth<128>(code, width, height, prx_orig, prx_pitch, prx_jac, jac_pitch, avg_dpt, dpt_out, dpt_pitch); return 0;
+    default: return -1;
+  }
+}
+
+}  // extern "C"

@@ -61,6 +61,12 @@ class DfkTrackLevel(C.Structure):
                 ("iterations", C.c_int)]
 
 
+class DfkWindowDesc(C.Structure):
+    _fields_ = [("num_keyframes", C.c_int32), ("num_pairs", C.c_int32), ("num_items", C.c_int32), ("code_size", C.c_int32),
+                ("pair_k0", C.POINTER(C.c_int32)), ("pair_k1", C.POINTER(C.c_int32)), ("item_pair", C.POINTER(C.c_int32)),
+                ("item_width", C.POINTER(C.c_int32)), ("item_height", C.POINTER(C.c_int32))]
+
+
 # every symbol include/dfk.h declares: (name, restype, argtypes)
 _F = C.POINTER(C.c_float)
 _IMG = C.POINTER(DfkImage)
@@ -89,6 +95,10 @@ SYMBOLS = {
                                          C.POINTER(C.c_uint64)]),
     "dfk_sfm_run_step_batch": (C.c_int, [_H, C.POINTER(DfkSfmWorkItem), C.c_int, C.c_int, C.c_void_p]),
     "dfk_sfm_run_step_batch_host": (C.c_int, [_H, C.POINTER(DfkSfmWorkItem), C.c_int, C.c_int, _F]),
+    "dfk_window_create": (C.c_int, [_H, C.POINTER(DfkWindowDesc), C.POINTER(C.c_void_p)]),
+    "dfk_window_destroy": (C.c_int, [_H, C.c_void_p]),
+    "dfk_window_floats": (C.c_size_t, [C.c_void_p]),
+    "dfk_window_assemble": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfk_se3_run_step": (C.c_int, [_H, _F, _CAM, _IMG, _IMG, _IMG, _IMG, _F, _F, _F, C.POINTER(C.c_uint64)]),
     "dfk_se3_track": (C.c_int, [_H, _F, C.POINTER(DfkTrackLevel), C.c_int, _F, _F, _F, _F, C.c_int]),
     "dfk_se3_warp": (C.c_int, [_H, _F, _CAM, _IMG, _IMG, _IMG, _IMG, _F, C.POINTER(C.c_uint64)]),

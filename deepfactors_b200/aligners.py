@@ -259,6 +259,55 @@ class SfmAligner:
         return [JTJJrReductionItem.from_record(r[i], self.CS) for i in range(r.shape[0])]
 
 
+# ------------------------------------------------------------------------------------------- keyframe window
+class Window:
+    """Device-side assembly of a keyframe window's block-sparse normal equations (dfk_window_* of include/dfk.h):
+    what the factor graph does with the RunStep records of a window -- PhotometricFactor::linearize's block slicing,
+    sign flip and residual rescale (sources/core/gtsam/photometric_factor.cpp:105-161,275-282) summed over the window's
+    factors (one per pair and level, core/mapping/df_work.cpp:211-225).  `layout` (factors.WindowBlocks) describes the
+    buffer; it is the one buffer a multi-GPU Gauss-Newton step all-reduces."""
+
+    def __init__(self, aligner: "SfmAligner", num_keyframes: int, pairs, item_pair, item_sizes):
+        from .factors import WindowBlocks
+        self._al = aligner
+        self.layout = WindowBlocks(int(num_keyframes), aligner.CS, [tuple(map(int, p)) for p in pairs])
+        k0 = np.ascontiguousarray([p[0] for p in self.layout.pairs], dtype=np.int32)
+        k1 = np.ascontiguousarray([p[1] for p in self.layout.pairs], dtype=np.int32)
+        ip = np.ascontiguousarray(item_pair, dtype=np.int32)
+        iw = np.ascontiguousarray([s[0] for s in item_sizes], dtype=np.int32)
+        ih = np.ascontiguousarray([s[1] for s in item_sizes], dtype=np.int32)
+        I32 = C.POINTER(C.c_int32)
+        desc = _lib.DfkWindowDesc(int(num_keyframes), len(k0), len(ip), aligner.CS, k0.ctypes.data_as(I32),
+                                  k1.ctypes.data_as(I32), ip.ctypes.data_as(I32), iw.ctypes.data_as(I32),
+                                  ih.ctypes.data_as(I32))
+        self.w = C.c_void_p()
+        check(aligner.handle, lib().dfk_window_create(aligner.handle, C.byref(desc), C.byref(self.w)))
+        self.num_items = len(ip)
+        self.floats = int(lib().dfk_window_floats(self.w))
+        assert self.floats == self.layout.floats
+
+    def assemble(self, records: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """records: [num_items, REC] device tensor written by RunStepBatch.  Asynchronous on torch's current stream."""
+        self._al._hd.use_torch_stream()
+        if out is None:
+            out = torch.empty(self.floats, dtype=torch.float32, device=records.device)
+        assert out.is_contiguous() and out.numel() >= self.floats and records.is_contiguous()
+        check(self._al.handle, lib().dfk_window_assemble(self._al.handle, self.w, C.c_void_p(records.data_ptr()),
+                                                         C.c_void_p(out.data_ptr())))
+        return out
+
+    def close(self):
+        if getattr(self, "w", None):
+            lib().dfk_window_destroy(self._al.handle, self.w)
+            self.w = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------------------------------- SE3Aligner
 class SE3Aligner:
     """df::SE3Aligner<float> (sources/cuda/cu_se3aligner.h:38-86)."""

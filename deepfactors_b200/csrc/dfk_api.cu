@@ -62,6 +62,15 @@ struct DfkContext {
   uint64_t launches = 0;
 };
 
+// CSR adjacency of a keyframe window on the device (dfk_window_create)
+struct DfkWindow {
+  int device = 0;
+  WindowDev dev{};
+  int* ints = nullptr;      // one allocation: kf0_ptr | kf0_items | kf1_ptr | kf1_items | pair_ptr | pair_items
+  float* areas = nullptr;
+  size_t floats = 0;
+};
+
 namespace {
 
 DfkStatus fail(DfkHandle h, DfkStatus s, const std::string& msg)
@@ -253,14 +262,10 @@ cudaError_t ensure(T** ptr, size_t* cap, size_t need)
   return e;
 }
 
-// floor(2^32 / b) for div_magic on the device (b == 1: 2^32 - 1, which the single correction step makes exact)
-uint32_t tc_magic(uint32_t b) { return b <= 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / b); }
-
-// tile_px == 0: block decomposition of the tensor-core kernel (see SfmItemDev::tc_*)
 DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, int tile_px, int max_ctas,
-                      const float* codes_dev, SfmLaunchPlan* plan)
+                      float* ray_tabs, const float* codes_dev, SfmLaunchPlan* plan)
 {
-  const bool tc = (tile_px == 0);
+  size_t ray_cursor = 0;
   const DfkDenseSfmParams& sp = h->params.sfmparams;
   h->items_host.resize(n);
   uint32_t tile_cursor = 0;
@@ -308,35 +313,18 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
       memcpy(h->codes_host.data() + (size_t)i * code_size, w.code, sizeof(float) * code_size);
     }
     d.width = W; d.height = H; d.num_pixels = W * H;
-    d.ray_tab = nullptr;
-    d.tc_ph = d.tc_ngroups = d.tc_npatches = 0;
-    d.tc_mag_ph = d.tc_mag_np = d.tc_mag_ng = 0;
-    if (tc) {
-      const uint32_t nstrips = (W + kTcBlockPixels - 1) / kTcBlockPixels;
-      d.tc_ngroups = (H + 31) / 32;
-      d.tc_ph = (H + d.tc_ngroups - 1) / d.tc_ngroups;  // <= 32 rows per patch, the last patch of a strip may run past H
-      d.tc_npatches = nstrips * d.tc_ngroups;
-      d.num_tiles = d.tc_npatches * d.tc_ph;
-      d.perm_mul = perm_multiplier(d.tc_npatches);
-      d.tc_mag_ph = tc_magic(d.tc_ph);
-      d.tc_mag_np = tc_magic(d.tc_npatches);
-      d.tc_mag_ng = tc_magic(d.tc_ngroups);
-      d.mag_tiles = 0;
-    } else {
-      d.num_tiles = (d.num_pixels + tile_px - 1) / tile_px;
-      d.perm_mul = perm_multiplier(d.num_tiles);
-      d.mag_tiles = (uint32_t)((1ull << 32) / d.num_tiles);
-    }
+    d.num_tiles = (d.num_pixels + tile_px - 1) / tile_px;
+    d.ray_tab = ray_tabs ? ray_tabs + ray_cursor : nullptr;
+    ray_cursor += (size_t)W + H;
     d.tile_begin = tile_cursor;
     tile_cursor += d.num_tiles;
+    d.perm_mul = perm_multiplier(d.num_tiles);
+    d.mag_tiles = (uint32_t)((1ull << 32) / d.num_tiles);
     d.mag_width = (uint32_t)((1ull << 32) / W);
     d.flags = 0;
-    // bulk copies (TMA engine) need 16-byte aligned sources and sizes; the tensor-core kernel stages only the code
-    // Jacobian that way (row segments of 32 pixels), the other kernels stage img0 / dpt0 as well
-    const bool bulk = tc ? (aligned(d.jac, 16) && (d.jac_pitch % 4 == 0) && (code_size % 4 == 0))
-                         : ((W % 4 == 0) && aligned(d.img0, 16) && aligned(d.dpt0, 16) && aligned(d.jac, 16) &&
-                            (d.img0_pitch % 4 == 0) && (d.dpt0_pitch % 4 == 0) && (d.jac_pitch % 4 == 0) &&
-                            (code_size % 4 == 0));
+    const bool bulk = (W % 4 == 0) && aligned(d.img0, 16) && aligned(d.dpt0, 16) && aligned(d.jac, 16) &&
+                      (d.img0_pitch % 4 == 0) && (d.dpt0_pitch % 4 == 0) && (d.jac_pitch % 4 == 0) &&
+                      (code_size % 4 == 0);
     if (bulk) d.flags |= ITEM_FLAG_BULK;
     if (aligned(d.grad1, 8) && d.grad1_pitch % 2 == 0) d.flags |= ITEM_FLAG_GRAD_ALIGNED;
     if (fused) d.flags |= ITEM_FLAG_FUSED_DEPTH;
@@ -428,7 +416,12 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
                     std::to_string(code_size));
   DeviceGuard guard(h->device);
   SfmLaunchPlan plan;
-  const int tile_px = tc ? 0 : (wide ? sfm_wide_tile_pixels(code_size) : kTilePixels);
+  if (tc) {
+    size_t ray_floats = 0;
+    for (int i = 0; i < n; ++i) ray_floats += (size_t)items[i].img0.width + items[i].img0.height;
+    DFK_CUDA(h, ensure(&h->ray_tabs_dev, &h->ray_tabs_cap, ray_floats), "[SfmAligner::RunStep] scratch allocation failed");
+  }
+  const int tile_px = tc ? kTcTilePixels : (wide ? sfm_wide_tile_pixels(code_size) : kTilePixels);
   bool any_fused = false;
   for (int i = 0; i < n; ++i) any_fused = any_fused || items[i].code != nullptr;
   if (any_fused) {
@@ -436,7 +429,8 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     h->codes_host.assign((size_t)n * code_size, 0.0f);
   }
   const int ctas_per_sm = tc ? 2 : (wide ? 1 : sfm_fp32_ctas_per_sm(code_size));
-  DfkStatus st = build_items(h, items, n, code_size, tile_px, ctas_per_sm * h->num_sms, h->codes_dev, &plan);
+  DfkStatus st = build_items(h, items, n, code_size, tile_px, ctas_per_sm * h->num_sms,
+                             tc ? h->ray_tabs_dev : nullptr, h->codes_dev, &plan);
   if (st != DFK_OK) return st;
   if (any_fused)
     DFK_CUDA(h, cudaMemcpyAsync(h->codes_dev, h->codes_host.data(), sizeof(float) * (size_t)n * code_size,
@@ -455,8 +449,9 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     if (ps != DFK_OK) return ps;
   }
   if (tc) {
-    DFK_CUDA(h, launch_sfm_tc(h->items_dev, plan, h->partials_dev, h->stream, ev0, ev1),
+    DFK_CUDA(h, launch_sfm_tc(h->items_dev, plan, h->ray_tabs_dev, h->partials_dev, h->stream, ev0, ev1),
              "[SfmAligner::RunStep] kernel launch failed");
+    h->launches += 1;  // ray-table kernel
   } else if (wide) {
     DFK_CUDA(h, launch_sfm_wide(code_size, h->items_dev, plan, h->partials_dev, h->stream, ev0, ev1),
              "[SfmAligner::RunStep] kernel launch failed");
@@ -1038,6 +1033,117 @@ DfkStatus dfk_squared_error(DfkHandle h, const DfkImage* a, const DfkImage* b, f
     *out = h->out_host[0];
     return DFK_OK;
   } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
+    return oom(h);
+  }
+}
+
+DfkStatus dfk_window_create(DfkHandle h, const DfkWindowDesc* d, DfkWindow** out)
+{
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!d || !out) return fail(h, DFK_ERR_INVALID_ARG, "[Window] null argument");
+    *out = nullptr;
+    const int K = d->num_keyframes, P = d->num_pairs, n = d->num_items;
+    if (K <= 0 || P <= 0 || n <= 0 || !d->pair_k0 || !d->pair_k1 || !d->item_pair || !d->item_width || !d->item_height)
+      return fail(h, DFK_ERR_INVALID_ARG, "[Window] empty window / null index array");
+    if (!dfk_sfm_supports_code_size(d->code_size))
+      return fail(h, DFK_ERR_UNSUPPORTED, "[Window] no RunStep kernel for code size " + std::to_string(d->code_size));
+    for (int p = 0; p < P; ++p)
+      if (d->pair_k0[p] < 0 || d->pair_k0[p] >= K || d->pair_k1[p] < 0 || d->pair_k1[p] >= K)
+        return fail(h, DFK_ERR_INVALID_ARG, "[Window] pair " + std::to_string(p) + " names a keyframe outside the window");
+    for (int i = 0; i < n; ++i)
+      if (d->item_pair[i] < 0 || d->item_pair[i] >= P || d->item_width[i] <= 0 || d->item_height[i] <= 0)
+        return fail(h, DFK_ERR_INVALID_ARG, "[Window] record " + std::to_string(i) + " names a pair outside the window");
+    // CSR lists in item order (the summation order of the gather kernel)
+    std::vector<int> kf0_ptr(K + 1, 0), kf1_ptr(K + 1, 0), pair_ptr(P + 1, 0);
+    for (int i = 0; i < n; ++i) {
+      const int p = d->item_pair[i];
+      kf0_ptr[d->pair_k0[p] + 1] += 1;
+      kf1_ptr[d->pair_k1[p] + 1] += 1;
+      pair_ptr[p + 1] += 1;
+    }
+    for (int k = 0; k < K; ++k) { kf0_ptr[k + 1] += kf0_ptr[k]; kf1_ptr[k + 1] += kf1_ptr[k]; }
+    for (int p = 0; p < P; ++p) pair_ptr[p + 1] += pair_ptr[p];
+    std::vector<int> kf0_items(n), kf1_items(n), pair_items(n);
+    {
+      std::vector<int> c0(kf0_ptr.begin(), kf0_ptr.end() - 1), c1(kf1_ptr.begin(), kf1_ptr.end() - 1),
+          cp(pair_ptr.begin(), pair_ptr.end() - 1);
+      for (int i = 0; i < n; ++i) {
+        const int p = d->item_pair[i];
+        kf0_items[c0[d->pair_k0[p]]++] = i;
+        kf1_items[c1[d->pair_k1[p]]++] = i;
+        pair_items[cp[p]++] = i;
+      }
+    }
+    std::vector<int> blob;
+    blob.reserve((size_t)2 * (K + 1) + (P + 1) + 3 * (size_t)n);
+    const size_t o_kf0p = 0;
+    blob.insert(blob.end(), kf0_ptr.begin(), kf0_ptr.end());
+    const size_t o_kf0i = blob.size();
+    blob.insert(blob.end(), kf0_items.begin(), kf0_items.end());
+    const size_t o_kf1p = blob.size();
+    blob.insert(blob.end(), kf1_ptr.begin(), kf1_ptr.end());
+    const size_t o_kf1i = blob.size();
+    blob.insert(blob.end(), kf1_items.begin(), kf1_items.end());
+    const size_t o_pp = blob.size();
+    blob.insert(blob.end(), pair_ptr.begin(), pair_ptr.end());
+    const size_t o_pi = blob.size();
+    blob.insert(blob.end(), pair_items.begin(), pair_items.end());
+    std::vector<float> areas(n);
+    for (int i = 0; i < n; ++i) areas[i] = (float)d->item_width[i] * (float)d->item_height[i];
+
+    DeviceGuard guard(h->device);
+    DfkWindow* w = new (std::nothrow) DfkWindow();
+    if (!w) return oom(h);
+    w->device = h->device;
+    cudaError_t e = cudaMalloc((void**)&w->ints, blob.size() * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&w->areas, areas.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(w->ints, blob.data(), blob.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(w->areas, areas.data(), areas.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(w->ints);
+      cudaFree(w->areas);
+      delete w;
+      return cuda_fail(h, e, "[Window] index upload failed");
+    }
+    w->dev.num_keyframes = K; w->dev.num_pairs = P; w->dev.num_items = n; w->dev.code_size = d->code_size;
+    w->dev.kf0_ptr = w->ints + o_kf0p; w->dev.kf0_items = w->ints + o_kf0i;
+    w->dev.kf1_ptr = w->ints + o_kf1p; w->dev.kf1_items = w->ints + o_kf1i;
+    w->dev.pair_ptr = w->ints + o_pp; w->dev.pair_items = w->ints + o_pi;
+    w->dev.item_area = w->areas;
+    const size_t B = 6 + (size_t)d->code_size;
+    w->floats = (size_t)K * (B * B + B) + (size_t)P * 6 * B + 2;
+    *out = w;
+    return DFK_OK;
+  } catch (...) {
+    return oom(h);
+  }
+}
+
+DfkStatus dfk_window_destroy(DfkHandle h, DfkWindow* w)
+{
+  (void)h;
+  if (!w) return DFK_OK;
+  DeviceGuard guard(w->device);
+  cudaFree(w->ints);
+  cudaFree(w->areas);
+  delete w;
+  return DFK_OK;
+}
+
+size_t dfk_window_floats(const DfkWindow* w) { return w ? w->floats : 0; }
+
+DfkStatus dfk_window_assemble(DfkHandle h, const DfkWindow* w, const float* records_dev, float* window_dev)
+{
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!w || !records_dev || !window_dev) return fail(h, DFK_ERR_INVALID_ARG, "[Window] null argument");
+    if (w->device != h->device) return fail(h, DFK_ERR_INVALID_ARG, "[Window] window and handle live on different devices");
+    DeviceGuard guard(h->device);
+    DFK_CUDA(h, launch_window_assemble(w->dev, records_dev, window_dev, h->stream), "[Window] kernel launch failed");
+    h->launches += 1;
+    return DFK_OK;
+  } catch (...) {
     return oom(h);
   }
 }

@@ -53,15 +53,8 @@ struct SfmItemDev {
   float* dpt_out;
   uint32_t dpt_out_pitch;
   const float* code;
-  // normalised ray tables in device scratch (unused since round 2: the tensor-core kernel evaluates Reproject's
-  // (p - c) / f itself, once per strip / row)
+  // normalised ray tables in device scratch: xn[0..width), then yn[0..height) (tensor-core kernel)
   const float* ray_tab;
-  // block decomposition of the tensor-core kernel (dfk_sfm_tc.cu): a block = 32 pixels of one image row, a patch =
-  // one 32-pixel-wide strip x tc_ph rows.  tile_begin / num_tiles count BLOCKS for that kernel (num_tiles =
-  // tc_npatches * tc_ph, including the null blocks below the last image row); block k of the item is row k % tc_ph of
-  // patch ((k / tc_ph) * perm_mul) % tc_npatches, patch p = strip p / tc_ngroups, row group p % tc_ngroups.
-  uint32_t tc_ph, tc_ngroups, tc_npatches;
-  uint32_t tc_mag_ph, tc_mag_np, tc_mag_ng;  // division magics (see tc_magic in dfk_api.cu)
   // relative-pose Jacobians (warping.h:120-134), row-major 6x6; used by the finalize kernel
   float P0[36];
   float P1[36];
@@ -80,7 +73,7 @@ struct SfmCfg {
 };
 
 constexpr int kTilePixels = 256;    // fp32 kernel
-constexpr int kTcBlockPixels = 32;  // tensor-core kernel: one block = 32 pixels of one image row
+constexpr int kTcTilePixels = 128;  // tensor-core kernel
 // tensor-core partial: rows = TMEM lanes that carry data (32 code-h, 32 code-l, 7 pose-h, 7 pose-l),
 // columns = B features (32 code, 7 pose/residual, 1 pad)
 constexpr int kTcRows = 78;
@@ -112,8 +105,9 @@ cudaError_t launch_sfm_wide(int code_size, const SfmItemDev* items_dev, const Sf
                             cudaEvent_t ev_stop = nullptr);
 // dfk_sfm_tc.cu
 bool sfm_tc_supported(int code_size);
-cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, float* partials_dev,
-                          cudaStream_t stream, cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr);
+cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, float* ray_tabs_dev,
+                          float* partials_dev, cudaStream_t stream, cudaEvent_t ev_start = nullptr,
+                          cudaEvent_t ev_stop = nullptr);
 size_t sfm_partial_floats(int code_size);
 // resident CTAs per SM of the fp32 kernel: at C = 8 a CTA is 11 warps and ~60 KB of shared memory, two fit (the front-end
 // is latency-bound, so the second CTA nearly doubles the throughput); from C = 16 on the register budget allows one
@@ -147,6 +141,19 @@ cudaError_t launch_blur_down(int in_w, int in_h, View in, int out_w, int out_h, 
                              cudaStream_t s);
 cudaError_t launch_squared_error(int width, int height, View a, View b, float* scratch, unsigned int* counter,
                                  float* out_dev, cudaStream_t s);
+// dfk_window.cu : block-sparse window assembly (gather over CSR lists built on the host by dfk_window_create)
+struct WindowDev {
+  int num_keyframes, num_pairs, num_items, code_size;
+  const int* kf0_ptr;     // [K+1] items whose keyframe (k0) is k ...
+  const int* kf0_items;   // ... in item order
+  const int* kf1_ptr;     // [K+1] items whose frame (k1) is k
+  const int* kf1_items;
+  const int* pair_ptr;    // [P+1] items of pair p (its levels)
+  const int* pair_items;
+  const float* item_area; // [n] W * H of the item's level
+};
+cudaError_t launch_window_assemble(const WindowDev& w, const float* records_dev, float* out_dev, cudaStream_t stream);
+
 constexpr int kSimpleMaxBlocks = 1024;
 constexpr int kSimpleScratchFloats = kSimpleMaxBlocks * 32;
 

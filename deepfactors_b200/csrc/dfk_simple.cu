@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "dfk_geom.cuh"
+#include "dfk_gn.cuh"
 #include "dfk_internal.h"
 
 namespace dfk {
@@ -95,86 +96,6 @@ __device__ __forceinline__ bool reduce_finalize(float (&v)[NV], unsigned int cnt
     }
   }
   if (threadIdx.x == 0) *counter = 0;  // self-resetting for the next launch on this stream
-  return true;
-}
-
-// ------------------------------------------------------------------------------ on-device Gauss-Newton update
-// camera_tracker.cpp:59-63: update = -JtJ.ldlt().solve(Jtr); translation += update.head<3>();
-// so3 = SO3::exp(update.tail<3>()) * so3.  Eigen's LDLT is a robust Cholesky with symmetric (diagonal) pivoting that
-// still returns a solution for semi-definite / ill-conditioned systems: pivots not larger than the smallest normal
-// float contribute nothing (Eigen's LDLT::solve zeroes those components).  Same here, so a rank-deficient level moves
-// the pose where the reference moves it, and an all-zero system (no inliers) leaves it alone.
-__device__ inline void ldlt6_solve(float A[6][6] /* full symmetric, destroyed */, const float b[6], float x[6])
-{
-  int perm[6];
-  for (int i = 0; i < 6; ++i) perm[i] = i;
-  for (int k = 0; k < 6; ++k) {
-    int p = k;
-    float best = fabsf(A[k][k]);
-    for (int i = k + 1; i < 6; ++i)
-      if (fabsf(A[i][i]) > best) {
-        best = fabsf(A[i][i]);
-        p = i;
-      }
-    if (p != k) {  // P A P^T: rows k <-> p (the finished L columns and the trailing block), then columns k <-> p
-      for (int c = 0; c < 6; ++c) { const float t = A[k][c]; A[k][c] = A[p][c]; A[p][c] = t; }
-      for (int r = 0; r < 6; ++r) { const float t = A[r][k]; A[r][k] = A[r][p]; A[r][p] = t; }
-      const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
-    }
-    const float d = A[k][k];
-    if (fabsf(d) > 1.17549435e-38f) {
-      float col[6];
-      for (int i = k + 1; i < 6; ++i) col[i] = A[i][k] / d;  // L_ik
-      for (int i = k + 1; i < 6; ++i)
-        for (int j = k + 1; j < 6; ++j) A[i][j] -= col[i] * A[j][k];  // A[j][k] still holds L_jk * d
-      for (int i = k + 1; i < 6; ++i) A[i][k] = col[i];
-    } else {
-      for (int i = k + 1; i < 6; ++i) A[i][k] = 0.0f;
-    }
-  }
-  float y[6];
-  for (int i = 0; i < 6; ++i) y[i] = b[perm[i]];
-  for (int i = 0; i < 6; ++i)
-    for (int k = 0; k < i; ++k) y[i] -= A[i][k] * y[k];
-  for (int i = 0; i < 6; ++i) y[i] = fabsf(A[i][i]) > 1.17549435e-38f ? y[i] / A[i][i] : 0.0f;
-  for (int i = 5; i >= 0; --i)
-    for (int k = i + 1; k < 6; ++k) y[i] -= A[k][i] * y[k];
-  for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
-}
-
-__device__ inline bool gn_update_pose(const float* __restrict__ sys /*21 JtJ packed upper, 6 Jtr*/, float* pose /*qx qy qz qw tx ty tz*/)
-{
-  float A[6][6], b[6];
-  int h = 0;
-  for (int r = 0; r < 6; ++r)
-    for (int c = r; c < 6; ++c) {
-      A[r][c] = sys[h];
-      A[c][r] = sys[h];
-      ++h;
-    }
-  for (int r = 0; r < 6; ++r) b[r] = -sys[21 + r];
-  float x[6];
-  ldlt6_solve(A, b, x);
-  // Sophus SO3::exp (quaternion form) and left multiplication, then renormalisation
-  const float th2 = x[3] * x[3] + x[4] * x[4] + x[5] * x[5];
-  const float th = sqrtf(th2);
-  float im, re;
-  if (th < 1e-10f) {
-    im = 0.5f - th2 * (1.0f / 48.0f) + th2 * th2 * (1.0f / 3840.0f);
-    re = 1.0f - 0.5f * th2 + th2 * th2 * (1.0f / 384.0f);
-  } else {
-    im = sinf(0.5f * th) / th;
-    re = cosf(0.5f * th);
-  }
-  const float ax = im * x[3], ay = im * x[4], az = im * x[5], aw = re;
-  const float bx = pose[0], by = pose[1], bz = pose[2], bw = pose[3];
-  float qx = aw * bx + ax * bw + ay * bz - az * by;
-  float qy = aw * by - ax * bz + ay * bw + az * bx;
-  float qz = aw * bz + ax * by - ay * bx + az * bw;
-  float qw = aw * bw - ax * bx - ay * by - az * bz;
-  const float n = sqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
-  pose[0] = qx / n; pose[1] = qy / n; pose[2] = qz / n; pose[3] = qw / n;
-  pose[4] += x[0]; pose[5] += x[1]; pose[6] += x[2];
   return true;
 }
 

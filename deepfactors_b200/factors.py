@@ -114,6 +114,83 @@ def assemble_window(layout: WindowLayout, pairs: Sequence[Tuple[int, int]], JtJ,
     return H, g, f
 
 
+@dataclass
+class WindowBlocks:
+    """The packed block-sparse buffer dfk_window_assemble writes (include/dfk.h): K diagonal blocks B x B,
+    K gradients B, P coupling blocks B x 6 ([pose0 | code0] of k0 x pose1 of k1), then f and the inlier total."""
+    num_keyframes: int
+    code_size: int
+    pairs: Sequence[Tuple[int, int]]
+
+    @property
+    def B(self) -> int:
+        return 6 + self.code_size
+
+    @property
+    def floats(self) -> int:
+        K, P, B = self.num_keyframes, len(self.pairs), self.B
+        return K * (B * B + B) + P * 6 * B + 2
+
+    def offsets(self):
+        K, P, B = self.num_keyframes, len(self.pairs), self.B
+        o_g = K * B * B
+        o_c = o_g + K * B
+        o_t = o_c + P * 6 * B
+        return o_g, o_c, o_t
+
+    def pack(self, item_pair, JtJ, Jtr, residual, inliers, sizes):
+        """Host mirror of dfk_window_assemble (numpy, float32 sums in item order): item i belongs to pair item_pair[i];
+        JtJ [n, NP, NP] dense, Jtr [n, NP], sizes[i] = (W, H).  Returns the flat buffer."""
+        K, B, c = self.num_keyframes, self.B, self.code_size
+        out = np.zeros(self.floats, dtype=np.float32)
+        o_g, o_c, o_t = self.offsets()
+        D = out[:o_g].reshape(K, B, B)
+        g = out[o_g:o_c].reshape(K, B)
+        O = out[o_c:o_t].reshape(len(self.pairs), B, 6)
+        loc0 = np.r_[0:6, 12:12 + c]  # [pose0 | code0] rows of a record
+        f = np.float32(0)
+        ninl = np.float32(0)
+        for i, p in enumerate(item_pair):
+            k0, k1 = self.pairs[p]
+            H = np.asarray(JtJ[i], dtype=np.float32)
+            r = np.asarray(Jtr[i], dtype=np.float32)
+            D[k0] += H[np.ix_(loc0, loc0)]
+            D[k1][:6, :6] += H[6:12, 6:12]
+            g[k0] -= r[loc0]
+            g[k1][:6] -= r[6:12]
+            O[p] += H[np.ix_(loc0, np.arange(6, 12))]
+            inl = int(inliers[i])
+            if inl > 0:
+                f += np.float32(residual[i]) / np.float32(inl) * np.float32(sizes[i][0] * sizes[i][1])
+            ninl += np.float32(inl)
+        out[o_t] = f
+        out[o_t + 1] = ninl
+        return out
+
+    def to_dense(self, buf):
+        """(H [dim, dim], g [dim], f, inliers) of the dense normal equations the buffer stands for (numpy float64, or
+        torch float64 on the buffer's device)."""
+        K, B = self.num_keyframes, self.B
+        o_g, o_c, o_t = self.offsets()
+        is_torch = hasattr(buf, "detach")
+        if is_torch:
+            import torch
+            b64 = buf.detach().to(torch.float64)
+            H = torch.zeros((K * B, K * B), dtype=torch.float64, device=buf.device)
+        else:
+            b64 = np.asarray(buf, dtype=np.float64)
+            H = np.zeros((K * B, K * B))
+        D = b64[:o_g].reshape(K, B, B)
+        for k in range(K):
+            H[k * B:(k + 1) * B, k * B:(k + 1) * B] += D[k]
+        O = b64[o_c:o_t].reshape(len(self.pairs), B, 6)
+        for p, (k0, k1) in enumerate(self.pairs):
+            H[k0 * B:(k0 + 1) * B, k1 * B:k1 * B + 6] += O[p]
+            H[k1 * B:k1 * B + 6, k0 * B:(k0 + 1) * B] += O[p].T if not is_torch else O[p].transpose(0, 1)
+        g = b64[o_g:o_c].reshape(K * B)
+        return H, g, float(b64[o_t]), float(b64[o_t + 1])
+
+
 def shard_pairs(num_pairs: int, world_size: int, rank: int) -> range:
     """Contiguous, balanced shard of the pair list for `rank` (sizes differ by at most one)."""
     lo = (num_pairs * rank) // world_size

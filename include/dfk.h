@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define DFK_VERSION 101
+#define DFK_VERSION 102
 
 typedef enum {
   DFK_OK = 0,
@@ -183,6 +183,43 @@ DfkStatus dfk_sfm_run_step_batch(DfkHandle h, const DfkSfmWorkItem* items, int n
 /* Same, then copies the records to host memory and synchronizes. */
 DfkStatus dfk_sfm_run_step_batch_host(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size,
                                       float* records_host);
+
+/* ------------------------------------------------------------------ keyframe window (block-sparse normal equations)
+ *
+ * What the factor graph does with the RunStep results of a window of keyframes: every (pair, level) result is one
+ * PhotometricFactor (sources/core/mapping/df_work.cpp:211-225) whose linearize() slices the (12+C)^2 Hessian into the
+ * blocks G11 G12 G13 G22 G23 G33 / g1 g2 g3 of a HessianFactor over (pose0, pose1, code0) with g = -Jtr and the
+ * residual rescaled to res / inliers * W * H (sources/core/gtsam/photometric_factor.cpp:105-161, 275-282); the solver
+ * then adds the factors of the window into one system.  dfk_window_assemble does that sum ON THE DEVICE, straight from
+ * the record buffer of dfk_sfm_run_step_batch, into a packed block-sparse buffer -- the one buffer a multi-GPU
+ * Gauss-Newton step all-reduces (pairs shard across GPUs, every rank assembles its own pairs into the same layout).
+ *
+ * Variables: keyframe k owns [pose_k (6) | code_k (C)], B = 6 + C.  Buffer layout (fp32):
+ *   K diagonal blocks  B x B, row-major, full symmetric
+ *   K gradients        B            (g = -sum Jtr)
+ *   P coupling blocks  B x 6, row-major: rows = [pose0 | code0] of the pair's keyframe k0, columns = pose1 of its k1
+ *   2 scalars          f = sum of rescaled residuals over items with overlap, total inliers (as a float)
+ * Deterministic: every output element is summed by one thread in item order (a gather, no float atomics).
+ */
+typedef struct DfkWindow DfkWindow;
+typedef struct {
+  int32_t num_keyframes;
+  int32_t num_pairs;
+  int32_t num_items;       /* records per evaluation: one per (pair, level) */
+  int32_t code_size;
+  const int32_t* pair_k0;  /* [num_pairs] keyframe (pose0 / code0) of every pair      (HOST arrays, copied) */
+  const int32_t* pair_k1;  /* [num_pairs] frame (pose1)                                                      */
+  const int32_t* item_pair;   /* [num_items] pair of every record                                            */
+  const int32_t* item_width;  /* [num_items] level size, for the residual rescale                            */
+  const int32_t* item_height;
+} DfkWindowDesc;
+DfkStatus dfk_window_create(DfkHandle h, const DfkWindowDesc* desc, DfkWindow** out);
+DfkStatus dfk_window_destroy(DfkHandle h, DfkWindow* w);
+/* floats of the block-sparse buffer: K*(B*B + B) + P*6*B + 2 */
+size_t dfk_window_floats(const DfkWindow* w);
+/* records_dev: num_items records as written by dfk_sfm_run_step_batch (DEVICE).  window_dev: dfk_window_floats()
+ * floats (DEVICE), fully overwritten.  Asynchronous on the handle's stream, one launch. */
+DfkStatus dfk_window_assemble(DfkHandle h, const DfkWindow* w, const float* records_dev, float* window_dev);
 
 /* ------------------------------------------------------------------ SE3Aligner */
 

@@ -10,6 +10,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -115,6 +117,70 @@ void dfko_sfm_run_step_f_omp(const float pose0[7], const float pose1[7], int cod
   }
   free(scratch);
   free(inl);
+}
+
+/* ------------------------------------------------------------------ throughput-mode CPU baseline (pthreads) */
+typedef struct {
+  int evals, loop_order, code_size, nlevels;
+  const float* pose0;
+  const float* pose1;
+  const DfkoLevel* levels;
+  const DfkoSfmParams* prm;
+  float* rec;  /* NH + NP + 2, thread-private */
+  double t_end;
+} ThroughputJob;
+
+static double now_s(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void* throughput_worker(void* arg)
+{
+  ThroughputJob* j = (ThroughputJob*)arg;
+  const int NP = 12 + j->code_size, NH = NP * (NP + 1) / 2;
+  for (int e = 0; e < j->evals; ++e)
+    for (int l = j->nlevels - 1; l >= 0; --l) { /* level 0 last: its record stays in rec */
+      const DfkoLevel* L = &j->levels[l];
+      uint64_t inl = 0;
+      dfko_sfm_run_step_f(j->pose0, j->pose1, j->code_size, &L->cam, L->width, L->height, L->img0, L->img0_pitch,
+                          L->img1, L->img1_pitch, L->dpt0, L->dpt0_pitch, NULL, 0, L->prx0_jac, L->jac_pitch,
+                          L->grad1, L->grad1_pitch, j->prm, j->loop_order, j->rec, j->rec + NH, j->rec + NH + NP, &inl);
+      j->rec[NH + NP + 1] = (float)inl;
+    }
+  j->t_end = now_s();
+  return NULL;
+}
+
+double dfko_sfm_throughput_f(int nthreads, int evals_per_thread, int loop_order, const float pose0[7],
+                             const float pose1[7], int code_size, int nlevels, const DfkoLevel* levels,
+                             const DfkoSfmParams* params, float* rec_out)
+{
+  if (nthreads < 1) nthreads = 1;
+  const int NP = 12 + code_size, NH = NP * (NP + 1) / 2, REC = NH + NP + 2;
+  ThroughputJob* jobs = (ThroughputJob*)calloc((size_t)nthreads, sizeof(ThroughputJob));
+  pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof(pthread_t));
+  float* recs = (float*)calloc((size_t)nthreads * REC, sizeof(float));
+  const double t0 = now_s();
+  for (int t = 0; t < nthreads; ++t) {
+    jobs[t].evals = evals_per_thread; jobs[t].loop_order = loop_order; jobs[t].code_size = code_size;
+    jobs[t].nlevels = nlevels; jobs[t].pose0 = pose0; jobs[t].pose1 = pose1; jobs[t].levels = levels;
+    jobs[t].prm = params; jobs[t].rec = recs + (size_t)t * REC; jobs[t].t_end = t0;
+    if (pthread_create(&th[t], NULL, throughput_worker, &jobs[t]) != 0) { /* run it here instead */
+      throughput_worker(&jobs[t]);
+      th[t] = 0;
+    }
+  }
+  double t1 = t0;
+  for (int t = 0; t < nthreads; ++t) {
+    if (th[t]) pthread_join(th[t], NULL);
+    if (jobs[t].t_end > t1) t1 = jobs[t].t_end;
+  }
+  if (rec_out) memcpy(rec_out, recs, sizeof(float) * REC);
+  free(recs); free(th); free(jobs);
+  return t1 - t0;
 }
 
 /* ------------------------------------------------------------------ UpdateDepth

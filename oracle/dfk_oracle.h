@@ -110,6 +110,24 @@ void dfko_sfm_run_step_f_omp(const float pose0[7], const float pose1[7], int cod
                              float* JtJ, float* Jtr, float* residual, uint64_t* inliers);
 int dfko_omp_max_threads(void);
 
+/* ---- CPU baseline in THROUGHPUT mode: `nthreads` POSIX threads, each evaluating the whole pyramid of one pair
+ * (`nlevels` RunStep calls, single-threaded, exactly dfko_sfm_run_step_f) `evals_per_thread` times on the same
+ * read-only inputs.  No OpenMP, no shared state: what N host cores can do with the reference's (single-threaded) CPU
+ * path.  Returns the wall time in seconds of the slowest thread (start of the first -> end of the last);
+ * rec_out (may be NULL) receives thread 0's last result for level 0: [JtJ | Jtr | residual | inliers-as-float]. */
+typedef struct {
+  DfkoCamera cam;
+  int width, height;
+  const float* img0; size_t img0_pitch;
+  const float* img1; size_t img1_pitch;
+  const float* dpt0; size_t dpt0_pitch;
+  const float* prx0_jac; size_t jac_pitch;
+  const float* grad1; size_t grad1_pitch;
+} DfkoLevel;
+double dfko_sfm_throughput_f(int nthreads, int evals_per_thread, int loop_order, const float pose0[7],
+                             const float pose1[7], int code_size, int nlevels, const DfkoLevel* levels,
+                             const DfkoSfmParams* params, float* rec_out);
+
 /* ---- SfmAligner::EvaluateError (cu_sfmaligner.cpp:120-147 + dense_sfm.h:79-119):
  * border 1 / min_dpt 0 defaults of FindCorrespondence, Huber-weighted sum of squares. */
 void dfko_sfm_evaluate_error_f(const float pose0[7], const float pose1[7], const DfkoCamera* cam,

@@ -306,5 +306,47 @@ def squared_error(a, b, precision="f32"):
     return float(fn(C.c_int(W), C.c_int(H), _ptr(a), _pitch(a), _ptr(b), _pitch(b)))
 
 
+class Level(C.Structure):
+    """DfkoLevel / RefLevel: one pyramid level of a pair for the throughput-mode CPU baselines"""
+    _fields_ = [("cam", Camera), ("width", C.c_int), ("height", C.c_int),
+                ("img0", C.POINTER(C.c_float)), ("img0_pitch", C.c_size_t),
+                ("img1", C.POINTER(C.c_float)), ("img1_pitch", C.c_size_t),
+                ("dpt0", C.POINTER(C.c_float)), ("dpt0_pitch", C.c_size_t),
+                ("prx0_jac", C.POINTER(C.c_float)), ("jac_pitch", C.c_size_t),
+                ("grad1", C.POINTER(C.c_float)), ("grad1_pitch", C.c_size_t)]
+
+
+def make_levels(levels):
+    """levels: objects with cam, img0, img1, dpt0, prx_jac, grad1 (deepfactors_b200.synth.PairLevel).  Returns the
+    ctypes array and the list of arrays it points into (keep both alive)."""
+    arr = (Level * len(levels))()
+    keep = []
+    for i, L in enumerate(levels):
+        a = [np.ascontiguousarray(_f32(x)) for x in (L.img0, L.img1, L.dpt0, L.prx_jac, L.grad1)]
+        keep.append(a)
+        H, W = a[0].shape
+        arr[i] = Level(_cam(L.cam), W, H, _ptr(a[0]), _pitch(a[0]), _ptr(a[1]), _pitch(a[1]), _ptr(a[2]), _pitch(a[2]),
+                       _ptr(a[3]), _pitch(a[3]), _ptr(a[4]), _pitch(a[4]))
+    return arr, keep
+
+
+def sfm_throughput(pose0, pose1, levels, nthreads, evals_per_thread, params=None, loop_order=1):
+    """`nthreads` POSIX threads x `evals_per_thread` whole-pyramid evaluations (single-threaded dfko_sfm_run_step_f
+    each).  Returns (wall seconds, StepResult of level 0 from thread 0)."""
+    params = params or default_params()
+    arr, keep = make_levels(levels)
+    Cs = keep[0][3].shape[2]
+    NP = 12 + Cs
+    NH = NP * (NP + 1) // 2
+    rec = np.zeros(NH + NP + 2, dtype=np.float32)
+    pose0 = np.ascontiguousarray(pose0, dtype=np.float32)
+    pose1 = np.ascontiguousarray(pose1, dtype=np.float32)
+    fn = lib().dfko_sfm_throughput_f
+    fn.restype = C.c_double
+    dt = fn(C.c_int(nthreads), C.c_int(evals_per_thread), C.c_int(loop_order), _ptr(pose0), _ptr(pose1), C.c_int(Cs),
+            C.c_int(len(levels)), arr, C.byref(params), _ptr(rec))
+    return float(dt), StepResult(rec[:NH].copy(), rec[NH:NH + NP].copy(), float(rec[NH + NP]), int(rec[NH + NP + 1]))
+
+
 def omp_max_threads() -> int:
     return int(lib().dfko_omp_max_threads())

@@ -16,7 +16,7 @@ import subprocess
 
 import numpy as np
 
-from .oracle import Camera, SfmParams, StepResult, _cam, _f32, _pitch, _ptr, default_params
+from .oracle import Camera, SfmParams, StepResult, _cam, _f32, _pitch, _ptr, default_params, make_levels
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libdfk_ref.so")
@@ -136,3 +136,23 @@ def update_depth(code, prx_orig, prx_jac, avg_dpt=2.0):
     if rc != 0:
         raise ValueError("code size not instantiated")
     return out
+
+
+def sfm_throughput(pose0, pose1, levels, nthreads, evals_per_thread, params=None):
+    """`nthreads` threads x `evals_per_thread` whole-pyramid evaluations through the reference's own host loop
+    (x outer / y inner, ut_sfmaligner.cpp:303-315).  Returns (wall seconds, StepResult of level 0 from thread 0)."""
+    params = params or default_params()
+    arr, keep = make_levels(levels)
+    Cs = keep[0][3].shape[2]
+    NP = 12 + Cs
+    NH = NP * (NP + 1) // 2
+    rec = np.zeros(NH + NP + 2, dtype=np.float32)
+    pose0 = np.ascontiguousarray(pose0, dtype=np.float32)
+    pose1 = np.ascontiguousarray(pose1, dtype=np.float32)
+    fn = lib().dfkr_sfm_throughput_f
+    fn.restype = C.c_double
+    dt = fn(C.c_int(nthreads), C.c_int(evals_per_thread), _ptr(pose0), _ptr(pose1), C.c_int(Cs), C.c_int(len(levels)), arr,
+            C.byref(params), _ptr(rec))
+    if dt < 0:
+        raise ValueError(f"code size {Cs} is not instantiated in oracle/ref_driver.cpp")
+    return float(dt), StepResult(rec[:NH].copy(), rec[NH:NH + NP].copy(), float(rec[NH + NP]), int(rec[NH + NP + 1]))

@@ -12,9 +12,12 @@
 // pin: the conventions restated in oracle/shim/ (getBilinear, quaternion rotate, SO3 product) -- see the shim headers.
 //
 // The C entry points mirror oracle/dfk_oracle.h (pitches in ELEMENTS of float) so the test can call both alike.
+#include <chrono>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include <Eigen/Core>
 #include <sophus/se3.hpp>
@@ -249,6 +252,50 @@ void dfkr_se3_run_step_f(const float se3[7], const Cam6* c, int width, int heigh
   for (int k = 0; k < 6; ++k) Jtr[k] = sum.Jtr(k);
   *residual = sum.residual;
   *inliers = sum.inliers;
+}
+
+// CPU baseline in THROUGHPUT mode (bench.py --impl reference): `nthreads` threads, each running the reference's own
+// single-threaded host loop (dfkr_sfm_run_step_f above, x outer / y inner as ut_sfmaligner.cpp:303-315) over the whole
+// pyramid of one pair `evals_per_thread` times on the same read-only inputs.  Same level struct as
+// oracle/dfk_oracle.h (DfkoLevel).  Returns the wall time in seconds; -1 for an uninstantiated code size.
+struct RefLevel {
+  Cam6 cam;
+  int width, height;
+  const float* img0; size_t img0_pitch;
+  const float* img1; size_t img1_pitch;
+  const float* dpt0; size_t dpt0_pitch;
+  const float* prx0_jac; size_t jac_pitch;
+  const float* grad1; size_t grad1_pitch;
+};
+double dfkr_sfm_throughput_f(int nthreads, int evals_per_thread, const float pose0[7], const float pose1[7],
+                             int code_size, int nlevels, const RefLevel* levels, const Params5* params, float* rec_out)
+{
+  if (!dfkr_supports_code_size(code_size)) return -1.0;
+  if (nthreads < 1) nthreads = 1;
+  const int NP = 12 + code_size, NH = NP * (NP + 1) / 2, REC = NH + NP + 2;
+  std::vector<float> recs((size_t)nthreads * REC, 0.0f);
+  std::vector<std::vector<float>> valid((size_t)nthreads);
+  auto worker = [&](int t) {
+    float* rec = recs.data() + (size_t)t * REC;
+    for (int e = 0; e < evals_per_thread; ++e)
+      for (int l = nlevels - 1; l >= 0; --l) {
+        const RefLevel& L = levels[l];
+        valid[t].assign((size_t)L.width * L.height, 0.0f);  // DenseSfm writes valid0 (dense_sfm.h:161): thread-private
+        uint64_t inl = 0;
+        dfkr_sfm_run_step_f(pose0, pose1, code_size, &L.cam, L.width, L.height, L.img0, L.img0_pitch, L.img1,
+                            L.img1_pitch, L.dpt0, L.dpt0_pitch, valid[t].data(), (size_t)L.width, L.prx0_jac, L.jac_pitch,
+                            L.grad1, L.grad1_pitch, params, rec, rec + NH, rec + NH + NP, &inl);
+        rec[NH + NP + 1] = (float)inl;
+      }
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(worker, t);
+  worker(0);
+  for (auto& x : th) x.join();
+  const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (rec_out) std::memcpy(rec_out, recs.data(), sizeof(float) * REC);
+  return dt;
 }
 
 // UpdateDepth's math (cu_image_proc.cpp:248-264, warping.h:52-69)

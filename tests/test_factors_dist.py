@@ -113,3 +113,56 @@ def test_two_rank_allreduce_equals_single_rank_window(oracle):
             Hr, gr = out[r]
             assert np.allclose(Hr, H_ref, rtol=1e-12, atol=1e-9 * np.abs(H_ref).max())
             assert np.allclose(gr, g_ref, rtol=1e-12, atol=1e-9 * np.abs(g_ref).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The packed block-sparse window buffer (what dfk_window_assemble writes on the device and ONE all-reduce sums):
+# host mirror factors.WindowBlocks vs the dense assembly, and the world_size-2 reduction of the packed buffers.
+def test_block_sparse_buffer_expands_to_the_dense_window(oracle):
+    pairs, H, g, res, inl, sizes = _window_systems(oracle, n_kf=3)
+    wb = factors.WindowBlocks(3, 8, pairs)
+    assert wb.floats == 3 * (14 * 14 + 14) + 3 * 6 * 14 + 2
+    buf = wb.pack(list(range(len(pairs))), H, g, res, inl, sizes)
+    Hd, gd, f, ninl = wb.to_dense(buf)
+    H_ref, g_ref, f_ref = factors.assemble_window(factors.WindowLayout(3, 8), pairs, H, g, res, inl, sizes)
+    assert np.allclose(Hd, H_ref, rtol=0, atol=2e-6 * np.abs(H_ref).max())   # fp32 buffer vs fp64 dense sums
+    assert np.allclose(gd, g_ref, rtol=0, atol=2e-6 * np.abs(g_ref).max())
+    assert abs(f - f_ref) <= 1e-5 * abs(f_ref) and ninl == float(inl.sum())
+    # two levels per pair: both records of a pair add into the same blocks
+    wb2 = factors.WindowBlocks(3, 8, pairs)
+    buf2 = wb2.pack([0, 0, 1, 1, 2, 2], np.concatenate([H[[0]], H[[0]], H[[1]], H[[1]], H[[2]], H[[2]]]),
+                    np.repeat(g, 2, axis=0), np.repeat(res, 2), np.repeat(inl, 2), [s for s in sizes for _ in range(2)])
+    assert np.allclose(buf2[:-2], 2 * buf[:-2], rtol=1e-6, atol=1e-6 * np.abs(buf).max())
+
+
+def _worker_sparse(rank, world, port, payload, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pairs, H, g, res, inl, sizes, n_kf, cs = payload
+        wb = factors.WindowBlocks(n_kf, cs, pairs)          # every rank: the SAME layout (all pairs of the window) ...
+        mine = list(factors.shard_pairs(len(pairs), world, rank))
+        buf = wb.pack(mine, H[mine], g[mine], res[mine], inl[mine], [sizes[i] for i in mine])  # ... filled from its shard
+        t = torch.from_numpy(buf)
+        dist.all_reduce(t)                                    # the ONE collective of a sharded Gauss-Newton step
+        out[rank] = t.numpy().copy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_allreduce_of_the_block_sparse_buffer(oracle):
+    pairs, H, g, res, inl, sizes = _window_systems(oracle, n_kf=4)
+    wb = factors.WindowBlocks(4, 8, pairs)
+    ref = wb.pack(list(range(len(pairs))), H, g, res, inl, sizes)
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker_sparse, args=(2, port, (pairs, H, g, res, inl, sizes, 4, 8), out), nprocs=2, join=True)
+        for r in range(2):
+            assert np.allclose(out[r], ref, rtol=1e-6, atol=1e-6 * np.abs(ref).max())
+        assert np.array_equal(out[0], out[1])
+    Hd, gd, f, _ = wb.to_dense(ref)
+    H_ref, g_ref, _ = factors.assemble_window(factors.WindowLayout(4, 8), pairs, H, g, res, inl, sizes)
+    assert np.allclose(Hd, H_ref, rtol=0, atol=2e-6 * np.abs(H_ref).max())

@@ -450,3 +450,43 @@ def test_error_reporting_is_loud(torch_mod):
     with pytest.raises((_lib.DfkError, ValueError)):
         bad.RunStep(pair.pose0, pair.pose1, None, L.cam, dev["img0"], dev["img1"], dev["dpt0"], None, dev["valid0"],
                     dev["prx0_jac"], dev["grad1"])
+
+
+@pytest.mark.gpu
+def test_window_assembly_on_device_matches_host_mirror():
+    """dfk_window_assemble (deterministic gather over the record buffer of a batch) == factors.WindowBlocks.pack on the
+    same records == the dense window of factors.assemble_window; 5 keyframes, 7 pairs x 2 levels, C = 32 and 8."""
+    import torch
+    from deepfactors_b200 import factors
+    from deepfactors_b200.aligners import SfmAligner, Window
+    for cs in (32, 8):
+        n_kf = 5
+        pairs = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 0), (0, 2), (3, 1)]
+        al = SfmAligner(cs)
+        items, item_pair, sizes = [], [], []
+        for p, (k0, k1) in enumerate(pairs):
+            pr = synth.make_pair(160, 120, cs, 2, seed=40 + p, code_sigma=0.2, phase=0.05 * p)
+            for L in pr.levels:
+                d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in dict(
+                    img0=L.img0, img1=L.img1, dpt0=L.dpt0, prx0_jac=L.prx_jac, grad1=L.grad1).items()}
+                items.append(dict(pose0=pr.pose0, pose1=pr.pose1, cam=L.cam, valid0=torch.zeros_like(d["img0"]), **d))
+                item_pair.append(p)
+                sizes.append((L.width, L.height))
+        work = al.make_work_items(items)
+        recs = al.RunStepBatch(work)
+        win = Window(al, n_kf, pairs, item_pair, sizes)
+        buf = win.assemble(recs)
+        buf2 = win.assemble(recs)
+        torch.cuda.synchronize()
+        assert torch.equal(buf, buf2)                                  # deterministic (a gather, no float atomics)
+        H, g, res, inl = factors.unpack_records(recs.cpu().numpy(), cs)
+        want = win.layout.pack(item_pair, H, g, res, inl, sizes)
+        got = buf.cpu().numpy()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()  # two fp32 summation orders of <= 6 terms
+        Hd, gd, f, ninl = win.layout.to_dense(got)
+        Hr, gr, fr = factors.assemble_window(factors.WindowLayout(n_kf, cs), [pairs[p] for p in item_pair], H, g, res, inl,
+                                             sizes)
+        assert np.abs(Hd - Hr).max() <= 2e-6 * np.abs(Hr).max() and np.abs(gd - gr).max() <= 2e-6 * np.abs(gr).max()
+        assert abs(f - fr) <= 1e-5 * abs(fr) and ninl == float(inl.sum())
+        assert np.allclose(Hd, Hd.T)

@@ -45,9 +45,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-step", type=int, default=8)
+    ap.add_argument("--config", default="pair8", choices=["pair8", "window200", "ba2k", "c128"],
+                    help="pair8 = BASELINE configs[1] (default, the metric's configuration); window200 = configs[2]; ba2k = "
+                         "configs[3] (run it with --gpus 8 under torchrun); c128 = configs[4]")
+    ap.add_argument("--pairs-per-step", type=int, default=0, help="override the pairs per GPU and step of a 'pairs' config")
     ap.add_argument("--gram", default="auto", choices=["auto", "fp32", "tf32x3"])
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--code-sigma", type=float, default=0.0,
@@ -302,19 +305,146 @@ def run_reference_arm(args):
     print(json.dumps(out))
 
 
+# ------------------------------------------------------------------------------------------------ e2e
+def run_e2e(args, al, base, host_levels, cs, dev, world, dist):
+    """The same metric through the reference-facing C-ABI call with HOST buffers: dfk_sfm_stream_submit / _wait
+    (include/dfk.h).  Every step uploads ALL inputs of one evaluation (4 levels x img0, img1, dpt0, prx_jac, grad1) from
+    pinned host memory, evaluates them and brings the 4 result records back to host memory; up to 3 submissions are in
+    flight, so the upload of evaluation k+1 overlaps the kernels of evaluation k (one synchronisation per wait)."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    from deepfactors_b200 import _lib
+    from deepfactors_b200._lib import DfkCamera, DfkImage, DfkSfmWorkItem
+
+    lib = _lib.lib()
+    rec_floats = _lib.record_floats(cs)
+    in_keys = ["img0", "img1", "prx0_jac", "grad1"] + (["prx_orig"] if args.fused_depth else ["dpt0"])
+    pinned = [{k: torch.from_numpy(np.ascontiguousarray(hl[k], dtype=np.float32)).pin_memory() for k in in_keys}
+              for hl in host_levels]
+    h2d = sum(int(t.numel()) * 4 for lv in pinned for t in lv.values())
+    d2h = LEVELS * rec_floats * 4
+
+    def himg(t, k=1):
+        H = t.shape[0]
+        W = t.shape[1] if t.dim() == 2 else t.shape[1]
+        return DfkImage(C.c_void_p(t.data_ptr()), t.stride(0) * 4, W, H)
+
+    arr = (DfkSfmWorkItem * LEVELS)()
+    code_keep = np.ascontiguousarray(base.code, dtype=np.float32)
+    for l, (L, pl) in enumerate(zip(base.levels, pinned)):
+        w = arr[l]
+        w.pose0 = (C.c_float * 7)(*np.asarray(base.pose0, dtype=np.float32).tolist())
+        w.pose1 = (C.c_float * 7)(*np.asarray(base.pose1, dtype=np.float32).tolist())
+        w.cam = DfkCamera(L.cam.fx, L.cam.fy, L.cam.u0, L.cam.v0, L.cam.width, L.cam.height)
+        w.img0, w.img1, w.prx0_jac, w.grad1 = himg(pl["img0"]), himg(pl["img1"]), himg(pl["prx0_jac"]), himg(pl["grad1"])
+        if args.fused_depth:
+            w.prx_orig = himg(pl["prx_orig"])
+            w.code = code_keep.ctypes.data_as(C.POINTER(C.c_float))
+        else:
+            w.dpt0 = himg(pl["dpt0"])
+    depth = 3
+    stream = C.c_void_p()
+    al._hd.use_torch_stream()
+    _lib.check(al.handle, lib.dfk_sfm_stream_create(al.handle, cs, LEVELS, h2d + (1 << 20), depth, C.byref(stream)))
+    out = np.zeros((LEVELS, rec_floats), dtype=np.float32)
+    outp = out.ctypes.data_as(C.POINTER(C.c_float))
+    tk = C.c_uint64(0)
+
+    def run(n):
+        waited = 0
+        for k in range(n):
+            if k - waited >= depth:
+                _lib.check(al.handle, lib.dfk_sfm_stream_wait(al.handle, stream, C.c_uint64(first + waited), outp))
+                waited += 1
+            _lib.check(al.handle, lib.dfk_sfm_stream_submit(al.handle, stream, arr, LEVELS, C.byref(tk)))
+        while waited < n:
+            _lib.check(al.handle, lib.dfk_sfm_stream_wait(al.handle, stream, C.c_uint64(first + waited), outp))
+            waited += 1
+
+    first = 0
+    run(3)              # warm-up (also sizes the handle's scratch)
+    first += 3
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n = max(1, args.e2e_steps)
+    t0 = time.perf_counter()
+    run(n)
+    e2e_dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    value = world * n / float(e2e_dt.item())
+    # the records that came back are the evaluation of the base pair: a cheap sanity check against a device-resident run
+    inl = int(out[0][-1:].view(np.uint32)[0])
+    lib.dfk_sfm_stream_destroy(al.handle, stream)
+    return {"value": value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n,
+            "gb_per_s_h2d": value / max(world, 1) * h2d / 1e9, "pipeline_depth": depth, "level0_inliers_returned": inl,
+            "note": "per step: dfk_sfm_stream_submit with HOST (pinned) image views of one evaluation -- every level's "
+                    "img0/img1/dpt0/prx_jac/grad1 uploaded on a copy stream, one batched launch for the 4 levels, the 4 "
+                    "result records downloaded -- and dfk_sfm_stream_wait; 3 submissions in flight"}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
+CONFIGS = {
+    # BASELINE.json configs[1], the metric's own configuration: 8 distinct pairs per GPU and step
+    "pair8": dict(kind="pairs", code=32, pairs_per_gpu=8,
+                  workload="single pair 640x480 4-level pyramid, code dim 32 (BASELINE configs[1]); {P} distinct pairs per "
+                           "GPU and step in one persistent launch"),
+    # configs[2]: one Gauss-Newton linearisation of a 50-keyframe window with 200 co-visibility pairs on one GPU
+    "window200": dict(kind="window", code=32, keyframes=50, pairs=200,
+                      workload="50-keyframe window, 200 co-visibility pairs (ring + random, seed 2), code dim 32, 640x480 "
+                               "4-level pyramids (BASELINE configs[2]); one step = one linearisation of the window"),
+    # configs[3]: global BA, pairs sharded over the GPUs, one all-reduce of the block-sparse Hessian per step
+    "ba2k": dict(kind="window", code=32, keyframes=200, pairs=2000,
+                 workload="200-keyframe global BA, 2000 pairs sharded over the GPUs, code dim 32, 640x480 4-level pyramids "
+                          "(BASELINE configs[3]); one step = one linearisation + the all-reduce of the block-sparse Hessian"),
+    # configs[4]: the code size the reference declares but cannot launch (cu_sfmaligner.cpp:170-173,210-211)
+    "c128": dict(kind="pairs", code=128, pairs_per_gpu=2,
+                 workload="single pair 640x480 4-level pyramid, code dim 128 (BASELINE configs[4]); {P} distinct pairs per "
+                          "GPU and step"),
+}
+
+
+def window_pairs(num_kf: int, num_pairs: int, seed: int = 2):
+    """ring neighbours first ((k, k+1), (k, k+2), ...), then random co-visibility pairs."""
+    import numpy as np
+    pairs, seen = [], set()
+    d = 1
+    while len(pairs) < min(num_pairs, num_kf * 5) and d <= 5:
+        for k in range(num_kf):
+            if len(pairs) >= num_pairs:
+                break
+            pr = (k, (k + d) % num_kf)
+            if pr not in seen:
+                seen.add(pr)
+                pairs.append(pr)
+        d += 1
+    rng = np.random.default_rng(seed)
+    while len(pairs) < num_pairs:
+        a, b = int(rng.integers(num_kf)), int(rng.integers(num_kf))
+        if a != b and (a, b) not in seen:
+            seen.add((a, b))
+            pairs.append((a, b))
+    return pairs
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference_arm(args)
         return
 
+    import ctypes as C
+
     import numpy as np
     import torch
     import torch.distributed as dist
 
     from deepfactors_b200 import _lib, synth
-    from deepfactors_b200.aligners import SfmAligner
+    from deepfactors_b200.aligners import SfmAligner, Window
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -326,49 +456,105 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
+    cfg = CONFIGS[args.config]
+    cs = cfg["code"]
+    if cfg["kind"] == "pairs" and args.pairs_per_step:
+        cfg = dict(cfg, pairs_per_gpu=args.pairs_per_step)
 
-    P = args.pairs_per_step
-    # ---- synthetic window: P distinct pairs resident in HBM -------------------------------------------
-    base = synth.make_pair(W0, H0, CS, LEVELS, seed=rank, code_sigma=args.code_sigma, identity_pose=args.identity_pose)
+    # ---- synthetic data resident in HBM ----------------------------------------------------------------------------
+    base = synth.make_pair(W0, H0, cs, LEVELS, seed=rank if cfg["kind"] == "pairs" else 0, code_sigma=args.code_sigma,
+                           identity_pose=args.identity_pose)
     host_levels = []
     for L in base.levels:
         host_levels.append(dict(img0=L.img0, img1=L.img1, dpt0=L.dpt0, prx0_jac=L.prx_jac, grad1=L.grad1))
         if args.fused_depth:
             host_levels[-1]["prx_orig"] = L.prx_orig
-    pairs_dev = []
-    for p in range(P):
-        lv = []
-        for L, hl in zip(base.levels, host_levels):
-            d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in hl.items()}
-            if p > 0:  # distinct contents per pair (device-side variation of the host-generated base pair)
-                d["prx0_jac"] = torch.roll(d["prx0_jac"], shifts=(3 * p, 5 * p), dims=(0, 1)).contiguous()
-                d["img0"] = (d["img0"] * (1.0 - 0.01 * p)).contiguous()
-            d["valid0"] = torch.zeros_like(d["img0"])
-            d["cam"] = L.cam
-            lv.append(d)
-        pairs_dev.append(lv)
+    base_dev = [{k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in hl.items()} for hl in host_levels]
 
-    al = SfmAligner(CS, gram_mode=args.gram)
-    items = []
-    for lv in pairs_dev:
-        for d in lv:
-            items.append(dict(pose0=base.pose0, pose1=base.pose1, cam=d["cam"], img0=d["img0"], img1=d["img1"],
-                              dpt0=d["dpt0"], valid0=d["valid0"], prx0_jac=d["prx0_jac"], grad1=d["grad1"]))
-            if args.fused_depth:
-                items[-1].update(prx_orig=d["prx_orig"], code=base.code)
+    def variant(l, q):
+        """inputs of level l, variation q (q = 0: the host-generated base): distinct contents per pair / keyframe made on
+        the device -- the code Jacobian rolled, img0 scaled.  bench_host_variant() repeats it on the host for --verify."""
+        d = dict(base_dev[l])
+        if q > 0:
+            d["prx0_jac"] = torch.roll(d["prx0_jac"], shifts=(3 * q, 5 * q), dims=(0, 1)).contiguous()
+            d["img0"] = (d["img0"] * (1.0 - 0.01 * (q % 50))).contiguous()
+        d["valid0"] = torch.zeros_like(d["img0"])
+        return d
+
+    def host_variant(l, q):
+        L = base.levels[l]
+        jac = np.roll(L.prx_jac, shift=(3 * q, 5 * q), axis=(0, 1)) if q > 0 else L.prx_jac
+        img0 = (L.img0 * np.float32(1.0 - 0.01 * (q % 50))).astype(np.float32) if q > 0 else L.img0
+        return np.ascontiguousarray(jac), img0
+
+    al = SfmAligner(cs, gram_mode=args.gram)
+    items, item_pair, item_sizes, item_src = [], [], [], []   # item_src: (variation of img0/jac side, level) for --verify
+    if cfg["kind"] == "pairs":
+        P = cfg["pairs_per_gpu"]            # pairs of THIS rank; the window of all ranks has world * P pairs
+        num_kf = 2 * P * world              # every pair brings its own keyframe and frame
+        all_pairs = [(2 * p, 2 * p + 1) for p in range(P * world)]
+        for p in range(P):
+            for l, L in enumerate(base.levels):
+                d = variant(l, p)
+                items.append(dict(pose0=base.pose0, pose1=base.pose1, cam=L.cam, img0=d["img0"], img1=d["img1"],
+                                  dpt0=d["dpt0"], valid0=d["valid0"], prx0_jac=d["prx0_jac"], grad1=d["grad1"]))
+                if args.fused_depth:
+                    items[-1].update(prx_orig=d["prx_orig"], code=base.code)
+                item_pair.append(rank * P + p)
+                item_sizes.append((L.width, L.height))
+                item_src.append((p, l))
+        scaling = "weak"
+    else:
+        num_kf = cfg["keyframes"]
+        all_pairs = window_pairs(num_kf, cfg["pairs"])
+        lo, hi = (len(all_pairs) * rank) // world, (len(all_pairs) * (rank + 1)) // world   # factors.shard_pairs
+        kfs = {}
+        for p in range(lo, hi):
+            for k in all_pairs[p]:
+                if k not in kfs:
+                    kfs[k] = [variant(l, k) for l in range(LEVELS)]   # keyframe k: its own buffers at every level
+        for p in range(lo, hi):
+            k0, k1 = all_pairs[p]
+            for l, L in enumerate(base.levels):
+                a, b = kfs[k0][l], kfs[k1][l]
+                items.append(dict(pose0=base.pose0, pose1=base.pose1, cam=L.cam, img0=a["img0"], img1=b["img1"],
+                                  dpt0=a["dpt0"], valid0=a["valid0"], prx0_jac=a["prx0_jac"], grad1=b["grad1"]))
+                if args.fused_depth:
+                    items[-1].update(prx_orig=a["prx_orig"], code=base.code)
+                item_pair.append(p)
+                item_sizes.append((L.width, L.height))
+                item_src.append((k0, l))
+        P = hi - lo
+        scaling = "strong"
     work = al.make_work_items(items)
-    rec_floats = _lib.record_floats(CS)
-    # window Hessian buffer: every rank owns P*LEVELS rows; all-reduce(sum) assembles the window
-    hess = torch.zeros((world * P * LEVELS, rec_floats), dtype=torch.float32, device=dev)
-    my_rows = hess[rank * P * LEVELS:(rank + 1) * P * LEVELS]
+    rec_floats = _lib.record_floats(cs)
+    n_items = len(items)
+    records = torch.zeros((n_items, rec_floats), dtype=torch.float32, device=dev)
+    # the window's block-sparse normal equations: every rank assembles ITS pairs into the layout of the WHOLE window, one
+    # all-reduce (sum) per step joins the ranks; two buffers so the collective of step i overlaps step i+1
+    win = Window(al, num_kf, all_pairs, item_pair, item_sizes)
+    wbuf = [torch.zeros(win.floats, dtype=torch.float32, device=dev) for _ in range(2)]
+    pending = [None, None]
+    step_no = [0]
 
     def step():
-        al.RunStepBatch(work, my_rows)
+        i = step_no[0] & 1
+        if pending[i] is not None:
+            pending[i].wait()           # the collective that last used this buffer (two steps ago): stream-side wait only
+            pending[i] = None
+        al.RunStepBatch(work, records)
+        win.assemble(records, wbuf[i])
         if world > 1:
-            dist.all_reduce(hess)
+            pending[i] = dist.all_reduce(wbuf[i], async_op=True)
+        step_no[0] += 1
+
+    def drain_comm():
+        for i in range(2):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
 
     lib = _lib.lib()
-    import ctypes as C
 
     def read_profile():
         ms, n, tot = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
@@ -377,6 +563,7 @@ def main():
 
     for _ in range(max(3, args.warmup)):
         step()
+    drain_comm()
     torch.cuda.synchronize()
     read_profile()
     _lib.check(al.handle, lib.dfk_set_profiling(al.handle, 1))
@@ -391,6 +578,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    drain_comm()                      # the last steps' all-reduces belong to the timed region
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -400,8 +588,14 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     kern_ms, kern_n, launches = read_profile()
-    # ---- sustained region: the same step, back to back, for >= --sustain-seconds (a 5 ms region is a sanity check, not a
-    # headline; this one is long enough for the clock / power state to settle and for NVML to see it)
+    pairs_all_ranks = torch.tensor([float(P)], device=dev)
+    if world > 1:
+        dist.all_reduce(pairs_all_ranks)
+    evals_per_step = float(pairs_all_ranks.item())
+    value = evals_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- sustained region: the same step, back to back, for >= --sustain-seconds (a few-ms region is a sanity check, not
+    # a headline; this one is long enough for the clock / power state to settle and for NVML to see it)
     sustained = None
     if args.sustain_seconds > 0:
         n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(total_ms / args.steps, 1e-3)) + 1)
@@ -412,6 +606,7 @@ def main():
         q0.record()
         for _ in range(n_sus):
             step()
+        drain_comm()
         q1.record()
         torch.cuda.synchronize()
         sms = torch.tensor([q0.elapsed_time(q1)], device=dev)
@@ -419,41 +614,42 @@ def main():
             dist.all_reduce(sms, op=dist.ReduceOp.MAX)
         sus_ms = float(sms.item())
         k2_ms, k2_n, _ = read_profile()
-        sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "value": world * P * n_sus / (sus_ms * 1e-3),
+        sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "value": evals_per_step * n_sus / (sus_ms * 1e-3),
                      "unit": "evals/s", "ms_per_step": sus_ms / n_sus,
                      "kernel_avg_launch_ms": (k2_ms / k2_n) if k2_n else None}
     clocks = sampler.stop() if rank == 0 else None
     _lib.check(al.handle, lib.dfk_set_profiling(al.handle, 0))
 
-    # ---- parity of the TIMED batch (outside the timed regions): the records the last step left in the window buffer for
-    # the first and the last pair of this rank, all 4 levels, against the CPU oracle (fp64) on the same inputs
+    # ---- parity of the TIMED batch (outside the timed regions): records of the first and the last pair of this rank, all
+    # levels, against the CPU oracle on the same inputs; and the window buffer against the host mirror of the assembly
     parity = None
     if rank == 0 and not args.no_verify:
+        from deepfactors_b200 import factors
         from oracle import oracle as orc
         orc.build()
-        recs_host = my_rows.detach().cpu().numpy() if world == 1 else None
-        if recs_host is None:  # the all-reduced buffer holds sums at N > 1: re-run the batch once into a private buffer
-            tmp = torch.zeros((P * LEVELS, rec_floats), dtype=torch.float32, device=dev)
-            al.RunStepBatch(work, tmp)
-            torch.cuda.synchronize()
-            recs_host = tmp.cpu().numpy()
-        NP = 12 + CS
+        al.RunStepBatch(work, records)          # a private evaluation: at N > 1 the window buffers hold reduced sums
+        chk = win.assemble(records)
+        torch.cuda.synchronize()
+        recs_host = records.cpu().numpy()
+        NP = 12 + cs
         NH = NP * (NP + 1) // 2
         worst_h, worst_g, inl_ok, checked, border_cases = 0.0, 0.0, True, 0, 0
         prm = orc.default_params()
-        for p in sorted({0, P - 1}):
-            for l, L in enumerate(base.levels):
-                jac = np.roll(L.prx_jac, shift=(3 * p, 5 * p), axis=(0, 1)) if p > 0 else L.prx_jac
-                img0 = (L.img0 * np.float32(1.0 - 0.01 * p)).astype(np.float32) if p > 0 else L.img0
+        first, last = 0, n_items - LEVELS
+        for it0 in sorted({first, last}):
+            for l in range(LEVELS):
+                i = it0 + l
+                q, lv = item_src[i]
+                L = base.levels[lv]
+                jac, img0 = host_variant(lv, q)
                 dpt0 = L.dpt0
                 if args.fused_depth:
                     dpt0 = orc.update_depth(base.code, L.prx_orig, jac, 2.0)
-                jacc = np.ascontiguousarray(jac)
-                o = orc.sfm_run_step(base.pose0, base.pose1, L.cam, img0, L.img1, dpt0, None, jacc, L.grad1, prm,
+                o = orc.sfm_run_step(base.pose0, base.pose1, L.cam, img0, L.img1, dpt0, None, jac, L.grad1, prm,
                                      precision="f64")
-                of = orc.sfm_run_step(base.pose0, base.pose1, L.cam, img0, L.img1, dpt0, None, jacc, L.grad1, prm,
+                of = orc.sfm_run_step(base.pose0, base.pose1, L.cam, img0, L.img1, dpt0, None, jac, L.grad1, prm,
                                       precision="f32")
-                r = recs_host[p * LEVELS + l]
+                r = recs_host[i]
                 inl = int(r[NH + NP + 1:NH + NP + 2].view(np.uint32)[0])
                 # inlier set: bit-exact against the fp32 CPU path (what the reference's own GPU-vs-CPU test demands,
                 # ut_sfmaligner.cpp:320).  fp64 can disagree with fp32 about pixels exactly on the border line (identity
@@ -466,91 +662,42 @@ def main():
                 worst_g = max(worst_g, float(np.abs(r[NH:NH + NP] - ref_o.Jtr).max()) /
                               (float(np.abs(ref_o.Jtr).max()) or 1.0) / scale)
                 checked += 1
+        Hh, gh, rh, ih = factors.unpack_records(recs_host, cs)
+        want = win.layout.pack(item_pair, Hh, gh, rh, ih, item_sizes)
+        got = chk.cpu().numpy()
+        win_err = float(np.abs(got - want).max() / (np.abs(want).max() or 1.0))
+        tol_h = 2e-5 if cs <= 32 else 4e-5
         parity = {"parity_checked": True, "records_checked": checked, "inliers_exact": bool(inl_ok),
                   "max_rel_err_JtJ_vs_f64": worst_h, "max_rel_err_Jtr_vs_f64": worst_g,
-                  "tolerance": {"JtJ": 2e-5, "Jtr": 1e-4},
-                  "ok": bool(inl_ok and worst_h <= 2e-5 and worst_g <= 1e-4),
+                  "tolerance": {"JtJ": tol_h, "Jtr": 1e-4, "window": 2e-6},
+                  "window_buffer_max_rel_err_vs_host_mirror": win_err,
+                  "ok": bool(inl_ok and worst_h <= tol_h and worst_g <= 1e-4 and win_err <= 2e-6),
                   "records_compared_with_fp32_flavour": border_cases,
-                  "what": f"pairs 0 and {P - 1} of the timed batch, levels 0-3: inliers vs the fp32 CPU path (exact), sums vs "
-                          "oracle fp64 (vs fp32 at twice the tolerance where fp64 and fp32 disagree on border pixels)"}
+                  "what": "first and last pair of the timed batch, all levels: inliers vs the fp32 CPU path (exact), sums vs "
+                          "oracle fp64 (vs fp32 at twice the tolerance where fp64 and fp32 disagree on border pixels); the "
+                          "assembled block-sparse window vs factors.WindowBlocks.pack on the same records"}
 
-    evals = world * P * args.steps
-    value = evals / (total_ms * 1e-3)
-
-    # ---- single pair per launch (latency-bound regime), rotating over the P pairs ----------------------
+    # ---- single pair per launch (latency-bound regime: what PhotometricFactor::linearize pays per factor) ---------------
     single = None
-    works1 = [al.make_work_items(items[p * LEVELS:(p + 1) * LEVELS]) for p in range(P)]
-    recs1 = torch.empty((LEVELS, rec_floats), dtype=torch.float32, device=dev)
-    for p in range(P):
-        al.RunStepBatch(works1[p], recs1)
-    torch.cuda.synchronize()
-    n1 = max(50, 4 * args.steps)
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for i in range(n1):
-        al.RunStepBatch(works1[i % P], recs1)
-    s1.record()
-    torch.cuda.synchronize()
-    single_ms = s0.elapsed_time(s1) / n1
-    single = {"pairs_per_launch": 1, "value": 1e3 / single_ms, "unit": "evals/s", "ms_per_eval": single_ms,
-              "frac_of_hbm_roofline": None}
+    if cfg["kind"] == "pairs":
+        works1 = [al.make_work_items(items[p * LEVELS:(p + 1) * LEVELS]) for p in range(P)]
+        recs1 = torch.empty((LEVELS, rec_floats), dtype=torch.float32, device=dev)
+        for p in range(P):
+            al.RunStepBatch(works1[p], recs1)
+        torch.cuda.synchronize()
+        n1 = max(50, 4 * args.steps)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n1):
+            al.RunStepBatch(works1[i % P], recs1)
+        s1.record()
+        torch.cuda.synchronize()
+        single_ms = s0.elapsed_time(s1) / n1
+        single = {"pairs_per_launch": 1, "value": 1e3 / single_ms, "unit": "evals/s", "ms_per_eval": single_ms,
+                  "frac_of_hbm_roofline": None}
 
-    # ---- e2e: synchronous reference-facing calls, every input uploaded from pinned host memory ----------
-    # the inputs of one evaluation live in ONE pinned host allocation and travel as ONE copy into one device allocation
-    # (the per-level tensors are 256-byte aligned views of it): 20 separate cudaMemcpyAsync calls cost ~40 % of the PCIe rate
-    in_keys = [k for k in host_levels[0].keys() if not (args.fused_depth and k == "dpt0")]  # fused: dpt0 is an output
-    layout, total = [], 0
-    for hl in host_levels:
-        ent = {}
-        for k in in_keys:
-            n = int(np.asarray(hl[k]).size)
-            ent[k] = (total, n, tuple(np.asarray(hl[k]).shape))
-            total += (n + 63) // 64 * 64
-        layout.append(ent)
-    host_blob = torch.empty(total, dtype=torch.float32).pin_memory()
-    dev_blob = torch.empty(total, dtype=torch.float32, device=dev)
-    stage = []
-    for hl, ent in zip(host_levels, layout):
-        sd = {}
-        for k, (off, n, shape) in ent.items():
-            host_blob[off:off + n].copy_(torch.from_numpy(np.ascontiguousarray(hl[k], dtype=np.float32)).reshape(-1))
-            sd[k] = dev_blob[off:off + n].view(shape)
-        if "dpt0" not in sd:
-            sd["dpt0"] = torch.empty(tuple(np.asarray(hl["dpt0"]).shape), dtype=torch.float32, device=dev)
-        sd["valid0"] = torch.zeros_like(sd["img0"])
-        stage.append(sd)
-    h2d = sum(n * 4 for ent in layout for (_, n, _) in ent.values())
-    d2h = LEVELS * rec_floats * 4
-
-    e2e_items = [dict(pose0=base.pose0, pose1=base.pose1, cam=L.cam, img0=sd["img0"], img1=sd["img1"], dpt0=sd["dpt0"],
-                      valid0=sd["valid0"], prx0_jac=sd["prx0_jac"], grad1=sd["grad1"],
-                      **(dict(prx_orig=sd["prx_orig"], code=base.code) if args.fused_depth else {}))
-                 for L, sd in zip(base.levels, stage)]
-    e2e_work = al.make_work_items(e2e_items)
-    e2e_rec_dev = torch.empty((LEVELS, rec_floats), dtype=torch.float32, device=dev)
-    e2e_rec_host = torch.empty((LEVELS, rec_floats), dtype=torch.float32).pin_memory()
-
-    def e2e_step():
-        # every input of the evaluation travels host -> device (pinned, async on the launch stream), one batched
-        # C-ABI launch evaluates the 4 levels, the 4 result records travel back and the host waits for them
-        dev_blob.copy_(host_blob, non_blocking=True)
-        al.RunStepBatch(e2e_work, e2e_rec_dev)
-        e2e_rec_host.copy_(e2e_rec_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return e2e_rec_host
-
-    e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_dt = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.e2e_steps / float(e2e_dt.item())
+    # ---- e2e: the same metric through the C-ABI streaming call with HOST buffers ---------------------------------------
+    e2e = run_e2e(args, al, base, host_levels, cs, dev, world, dist)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -559,44 +706,48 @@ def main():
             peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        bytes_per_eval = PIXELS * (BYTES_PER_PX + (4 if args.fused_depth else 0))
+        bytes_per_px = 24 + 4 * cs + (4 if args.fused_depth else 0)
+        bytes_per_eval = PIXELS * bytes_per_px
         bytes_per_launch = P * bytes_per_eval
         traffic = None  # dram__bytes_read+write of one step-kernel launch, from the committed ncu --set full capture
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and P == 8 and args.gram in ("auto", "tf32x3") and not args.fused_depth:
+        if os.path.exists(tpath) and args.config == "pair8" and P == 8 and args.gram in ("auto", "tf32x3") and not args.fused_depth:
             traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = bytes_per_launch / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
-        single["frac_of_hbm_roofline"] = (bytes_per_eval / (single_ms * 1e-3) / 1e9) / peak
+        if single is not None:
+            single["frac_of_hbm_roofline"] = (bytes_per_eval / (single["ms_per_eval"] * 1e-3) / 1e9) / peak
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and cs == 32:
             cpu, _ = cpu_baseline(args.cpu_seconds, args.code_sigma, args.identity_pose)
         out = {
-            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": n_gpus, "steps": args.steps,
+            "metric": METRIC if cs == 32 else METRIC.replace("C=32", f"C={cs}"), "value": value, "unit": "evals/s",
+            "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "single pair 640x480 4-level pyramid, code dim 32 (BASELINE configs[1]); "
-                                   f"{P} distinct pairs per step in one persistent launch",
-                       "evals_per_step_per_gpu": P, "pixels_per_eval": PIXELS,
-                       "algorithmic_bytes_per_eval": bytes_per_eval, "gram": args.gram,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"name": args.config, "workload": cfg["workload"].format(P=P),
+                       "evals_per_step_per_gpu": P, "evals_per_step": evals_per_step, "pixels_per_eval": PIXELS,
+                       "algorithmic_bytes_per_eval": bytes_per_eval, "gram": args.gram, "code_size": cs,
                        "fused_depth_decode": bool(args.fused_depth),
                        "poses": "identity (100% inliers)" if args.identity_pose else
                                 "tests/ut_sfmaligner.cpp:254-264 (~60% inliers)",
                        "code_sigma": args.code_sigma,
-                       "l2": f"inputs larger than L2: each step streams {P * BYTES_PER_EVAL / 1e6:.0f} MB of distinct "
-                             "pair data (> 126 MB L2)",
-                       "parallelism": f"pairs sharded over {n_gpus} GPU(s)" + (
-                           "; one NCCL all-reduce of the window's normal equations per step" if world > 1 else "")},
+                       "window": {"keyframes": num_kf, "pairs": len(all_pairs), "block_sparse_floats": win.floats,
+                                  "block_sparse_bytes": 4 * win.floats},
+                       "l2": f"inputs larger than L2: each step streams {P * bytes_per_eval / 1e6:.0f} MB of pair data per GPU "
+                             "(> 126 MB L2)" if P * bytes_per_eval > 126e6 else
+                             f"{P * bytes_per_eval / 1e6:.0f} MB of pair data per step and GPU",
+                       "parallelism": f"pairs sharded over {n_gpus} GPU(s); every step assembles the window's block-sparse "
+                                      "normal equations on the device" + (
+                           "; ONE NCCL all-reduce of that buffer per step, asynchronous, overlapped with the next step's "
+                           "launch" if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "kernel": "sfm_step kernel (per-tile warp + Gram)", "launches_timed": kern_n,
                          "avg_launch_ms": kern_avg_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "note": "per step: every level's img0/img1/dpt0/prx_jac/grad1 copied "
-                    "from pinned host memory (one packed allocation, one async copy on the launch stream), one "
-                    "dfk_sfm_run_step_batch call for the 4 levels, the 4 result records copied back and waited for"},
+            "e2e": e2e,
             "single_launch": single,
             "sustained": sustained,
             "parity": parity,

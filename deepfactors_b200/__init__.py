@@ -10,7 +10,7 @@ from __future__ import annotations
 import importlib
 
 __all__ = ["aligners", "synth", "se3", "SfmAligner", "SE3Aligner"]
-_LAZY = {"SfmAligner": "aligners", "SE3Aligner": "aligners", "SfmAlignerParams": "aligners",
+_LAZY = {"SfmAligner": "aligners", "SE3Aligner": "aligners", "DepthAligner": "aligners", "Window": "aligners", "SfmAlignerParams": "aligners",
          "DenseSfmParams": "aligners", "UpdateDepth": "aligners", "SobelGradients": "aligners",
          "GaussianBlurDown": "aligners", "SquaredError": "aligners"}
 

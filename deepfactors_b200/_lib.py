@@ -95,6 +95,10 @@ SYMBOLS = {
                                          C.POINTER(C.c_uint64)]),
     "dfk_sfm_run_step_batch": (C.c_int, [_H, C.POINTER(DfkSfmWorkItem), C.c_int, C.c_int, C.c_void_p]),
     "dfk_sfm_run_step_batch_host": (C.c_int, [_H, C.POINTER(DfkSfmWorkItem), C.c_int, C.c_int, _F]),
+    "dfk_sfm_stream_create": (C.c_int, [_H, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "dfk_sfm_stream_destroy": (C.c_int, [_H, C.c_void_p]),
+    "dfk_sfm_stream_submit": (C.c_int, [_H, C.c_void_p, C.POINTER(DfkSfmWorkItem), C.c_int, C.POINTER(C.c_uint64)]),
+    "dfk_sfm_stream_wait": (C.c_int, [_H, C.c_void_p, C.c_uint64, _F]),
     "dfk_window_create": (C.c_int, [_H, C.POINTER(DfkWindowDesc), C.POINTER(C.c_void_p)]),
     "dfk_window_destroy": (C.c_int, [_H, C.c_void_p]),
     "dfk_window_floats": (C.c_size_t, [C.c_void_p]),
@@ -102,6 +106,7 @@ SYMBOLS = {
     "dfk_se3_run_step": (C.c_int, [_H, _F, _CAM, _IMG, _IMG, _IMG, _IMG, _F, _F, _F, C.POINTER(C.c_uint64)]),
     "dfk_se3_track": (C.c_int, [_H, _F, C.POINTER(DfkTrackLevel), C.c_int, _F, _F, _F, _F, C.c_int]),
     "dfk_se3_warp": (C.c_int, [_H, _F, _CAM, _IMG, _IMG, _IMG, _IMG, _F, C.POINTER(C.c_uint64)]),
+    "dfk_depth_run_step": (C.c_int, [_H, _F, C.c_int, _IMG, _IMG, _IMG, _F, _F, _F, C.POINTER(C.c_uint64)]),
     "dfk_update_depth": (C.c_int, [_H, _F, C.c_int, _IMG, _IMG, C.c_float, _IMG]),
     "dfk_sobel_gradients": (C.c_int, [_H, _IMG, _IMG]),
     "dfk_gaussian_blur_down": (C.c_int, [_H, _IMG, _IMG]),

@@ -259,6 +259,36 @@ class SfmAligner:
         return [JTJJrReductionItem.from_record(r[i], self.CS) for i in range(r.shape[0])]
 
 
+# ------------------------------------------------------------------------------------------- DepthAligner
+class DepthAligner:
+    """df::DepthAligner<float, CS> (sources/cuda/cu_depthaligner.h:38-54): code-only alignment of the decoded depth to a
+    target depth map; the result is a JTJJrReductionItem over the CS code parameters."""
+
+    def __init__(self, code_size: int, device=None):
+        self.CS = int(code_size)
+        self._hd = _Handle(device)
+
+    @property
+    def handle(self):
+        return self._hd.h
+
+    def RunStep(self, code, target_dpt, prx_orig, prx_jac) -> JTJJrReductionItem:
+        self._hd.use_torch_stream()
+        code = np.ascontiguousarray(code, dtype=np.float32)
+        if code.shape != (self.CS,):
+            raise ValueError(f"code must have {self.CS} entries")
+        nh = self.CS * (self.CS + 1) // 2
+        JtJ = np.zeros(nh, dtype=np.float32)
+        Jtr = np.zeros(self.CS, dtype=np.float32)
+        res, inl = C.c_float(0), C.c_uint64(0)
+        t, p, j = _image(target_dpt), _image(prx_orig), _image(prx_jac, self.CS)
+        FP = C.POINTER(C.c_float)
+        check(self._hd.h, lib().dfk_depth_run_step(self._hd.h, code.ctypes.data_as(FP), self.CS, C.byref(t), C.byref(p),
+                                                  C.byref(j), JtJ.ctypes.data_as(FP), Jtr.ctypes.data_as(FP),
+                                                  C.byref(res), C.byref(inl)))
+        return JTJJrReductionItem(JtJ, Jtr, float(res.value), int(inl.value))
+
+
 # ------------------------------------------------------------------------------------------- keyframe window
 class Window:
     """Device-side assembly of a keyframe window's block-sparse normal equations (dfk_window_* of include/dfk.h):

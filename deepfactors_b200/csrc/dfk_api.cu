@@ -62,6 +62,26 @@ struct DfkContext {
   uint64_t launches = 0;
 };
 
+// pipelined host -> device -> host evaluation (dfk_sfm_stream_*)
+struct DfkSfmStream {
+  int device = 0, code_size = 0, max_items = 0, depth = 0;
+  size_t max_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  struct Slot {
+    unsigned char* dev = nullptr;   // staged inputs (+ valid0 / decoded-depth scratch)
+    size_t cap = 0;
+    float* rec_dev = nullptr;
+    float* rec_host = nullptr;      // pinned
+    cudaEvent_t uploaded = nullptr, done = nullptr;
+    int n = 0;
+    uint64_t ticket = 0;
+    bool busy = false;
+  };
+  std::vector<Slot> slots;
+  std::vector<DfkSfmWorkItem> dev_items;  // scratch of submit()
+  uint64_t next_ticket = 0, next_wait = 0;
+};
+
 // CSR adjacency of a keyframe window on the device (dfk_window_create)
 struct DfkWindow {
   int device = 0;
@@ -1142,6 +1162,227 @@ DfkStatus dfk_window_assemble(DfkHandle h, const DfkWindow* w, const float* reco
     DeviceGuard guard(h->device);
     DFK_CUDA(h, launch_window_assemble(w->dev, records_dev, window_dev, h->stream), "[Window] kernel launch failed");
     h->launches += 1;
+    return DFK_OK;
+  } catch (...) {
+    return oom(h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- streaming from host
+DfkStatus dfk_sfm_stream_create(DfkHandle h, int code_size, int max_items, size_t max_bytes, int depth, DfkSfmStream** out)
+{
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!out || max_items <= 0 || max_bytes == 0 || depth < 1 || depth > 16)
+      return fail(h, DFK_ERR_INVALID_ARG, "[SfmStream] bad argument (1 <= depth <= 16, max_items > 0, max_bytes > 0)");
+    *out = nullptr;
+    if (!dfk_sfm_supports_code_size(code_size))
+      return fail(h, DFK_ERR_UNSUPPORTED, "[SfmStream] no RunStep kernel for code size " + std::to_string(code_size));
+    DeviceGuard guard(h->device);
+    DfkSfmStream* s = new (std::nothrow) DfkSfmStream();
+    if (!s) return oom(h);
+    s->device = h->device; s->code_size = code_size; s->max_items = max_items; s->depth = depth;
+    // initial slot size (a hint): staged images are padded to a 256-byte row pitch and offset, scratch images (valid0,
+    // decoded depth) ride along; a submission that needs more grows its slot
+    s->max_bytes = max_bytes + max_bytes / 4 + (size_t)max_items * 8 * 4096;
+    s->slots.resize(depth);
+    s->dev_items.resize(max_items);
+    const size_t rec = (size_t)DFK_SFM_RECORD_FLOATS(code_size) * max_items * sizeof(float);
+    cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < depth && e == cudaSuccess; ++k) {
+      DfkSfmStream::Slot& sl = s->slots[k];
+      e = cudaMalloc((void**)&sl.dev, s->max_bytes);
+      if (e == cudaSuccess) sl.cap = s->max_bytes;
+      if (e == cudaSuccess) e = cudaMalloc((void**)&sl.rec_dev, rec);
+      if (e == cudaSuccess) e = cudaMallocHost((void**)&sl.rec_host, rec);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.uploaded, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+      dfk_sfm_stream_destroy(h, s);
+      return cuda_fail(h, e, "[SfmStream] allocation failed");
+    }
+    *out = s;
+    return DFK_OK;
+  } catch (...) {
+    return oom(h);
+  }
+}
+
+DfkStatus dfk_sfm_stream_destroy(DfkHandle h, DfkSfmStream* s)
+{
+  (void)h;
+  if (!s) return DFK_OK;
+  DeviceGuard guard(s->device);
+  if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+  for (auto& sl : s->slots) {
+    if (sl.done) { cudaEventSynchronize(sl.done); cudaEventDestroy(sl.done); }
+    if (sl.uploaded) cudaEventDestroy(sl.uploaded);
+    cudaFree(sl.dev);
+    cudaFree(sl.rec_dev);
+    if (sl.rec_host) cudaFreeHost(sl.rec_host);
+  }
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  delete s;
+  return DFK_OK;
+}
+
+DfkStatus dfk_sfm_stream_submit(DfkHandle h, DfkSfmStream* s, const DfkSfmWorkItem* items, int n, uint64_t* ticket)
+{
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!s || !items || !ticket || n <= 0) return fail(h, DFK_ERR_INVALID_ARG, "[SfmStream] null argument / empty submission");
+    if (n > s->max_items) return fail(h, DFK_ERR_INVALID_ARG, "[SfmStream] more work items than the stream was created for");
+    if (s->device != h->device) return fail(h, DFK_ERR_INVALID_ARG, "[SfmStream] stream and handle live on different devices");
+    DfkSfmStream::Slot& sl = s->slots[s->next_ticket % (uint64_t)s->depth];
+    if (sl.busy)
+      return fail(h, DFK_ERR_INVALID_ARG,
+                  "[SfmStream] " + std::to_string(s->depth) + " submissions outstanding: wait for ticket " +
+                      std::to_string(sl.ticket) + " first");
+    DeviceGuard guard(h->device);
+    cudaError_t err = cudaSuccess;
+    // one image: host view -> 256-byte aligned, 256-byte pitched device view inside the slot.  upload == false: device
+    // scratch.  Two passes over the items: sizes first (the slot grows if it has to), then the copies.
+    for (int pass = 0; pass < 2; ++pass) {
+      size_t cursor = 0;
+      auto stage = [&](const DfkImage& src, uint32_t floats_per_px, bool upload) -> DfkImage {
+        DfkImage d{};
+        const size_t row = (size_t)src.width * floats_per_px * sizeof(float);
+        // rows that are already 16-byte multiples stay dense on the device (what the bulk-copy loaders of the kernels
+        // need), so a dense host image travels as ONE linear copy: per-row DMA descriptors cost ~30 % of the PCIe rate on
+        // the small pyramid levels; odd widths get a 256-byte pitch and a 2-D copy
+        const size_t pitch = (row % 16 == 0) ? row : ((row + 255) & ~(size_t)255);
+        cursor = (cursor + 255) & ~(size_t)255;
+        d.ptr = sl.dev + cursor;
+        d.pitch_bytes = pitch;
+        d.width = src.width;
+        d.height = src.height;
+        cursor += pitch * src.height;
+        if (pass == 1 && upload && err == cudaSuccess) {
+          if (pitch == row && src.pitch_bytes == row)
+            err = cudaMemcpyAsync(d.ptr, src.ptr, row * src.height, cudaMemcpyHostToDevice, s->copy_stream);
+          else
+            err = cudaMemcpy2DAsync(d.ptr, pitch, src.ptr, src.pitch_bytes, row, src.height, cudaMemcpyHostToDevice,
+                                    s->copy_stream);
+        }
+        return d;
+      };
+      for (int i = 0; i < n; ++i) {
+        const DfkSfmWorkItem& w = items[i];
+        const uint32_t W = w.img0.width, H = w.img0.height;
+        const bool fused = w.code != nullptr;
+        if (pass == 0 && (W == 0 || H == 0 || !img_ok(&w.img0, W, H, 1) || !img_ok(&w.img1, W, H, 1) ||
+                          !img_ok(&w.prx0_jac, W, H, s->code_size) || !img_ok(&w.grad1, W, H, 2) ||
+                          (fused ? !img_ok(&w.prx_orig, W, H, 1) : !img_ok(&w.dpt0, W, H, 1))))
+          return fail(h, DFK_ERR_INVALID_ARG, "[SfmStream] inconsistent host image views in work item " + std::to_string(i));
+        DfkSfmWorkItem& d = s->dev_items[i];
+        d = w;
+        d.img0 = stage(w.img0, 1, true);
+        d.img1 = stage(w.img1, 1, true);
+        d.prx0_jac = stage(w.prx0_jac, (uint32_t)s->code_size, true);
+        d.grad1 = stage(w.grad1, 2, true);
+        const DfkImage scalar = w.img0;  // geometry of a scalar scratch image
+        d.valid0 = stage(scalar, 1, false);
+        if (fused) {
+          d.prx_orig = stage(w.prx_orig, 1, true);
+          d.dpt0 = stage(scalar, 1, false);  // the decoded depth stays on the device
+        } else {
+          d.dpt0 = stage(w.dpt0, 1, true);
+        }
+      }
+      if (pass == 0 && cursor > sl.cap) {  // the slot is idle (not busy): its memory can be replaced
+        cudaFree(sl.dev);
+        sl.dev = nullptr;
+        sl.cap = 0;
+        DFK_CUDA(h, cudaMalloc((void**)&sl.dev, cursor), "[SfmStream] slot allocation failed");
+        sl.cap = cursor;
+      }
+    }
+    if (err != cudaSuccess) return cuda_fail(h, err, "[SfmStream] upload failed");
+    DFK_CUDA(h, cudaEventRecord(sl.uploaded, s->copy_stream), "[SfmStream] event record failed");
+    DFK_CUDA(h, cudaStreamWaitEvent(h->stream, sl.uploaded, 0), "[SfmStream] stream wait failed");
+    DfkStatus st = run_batch(h, s->dev_items.data(), n, s->code_size, sl.rec_dev);
+    if (st != DFK_OK) return st;
+    DFK_CUDA(h, cudaMemcpyAsync(sl.rec_host, sl.rec_dev, (size_t)DFK_SFM_RECORD_FLOATS(s->code_size) * n * sizeof(float),
+                                cudaMemcpyDeviceToHost, h->stream),
+             "[SfmStream] result download failed");
+    DFK_CUDA(h, cudaEventRecord(sl.done, h->stream), "[SfmStream] event record failed");
+    // the NEXT use of this slot's staging memory (depth submissions later) is host-ordered behind wait(ticket); the copy
+    // stream itself must not run ahead of the evaluation that still reads the slot it is about to overwrite
+    sl.busy = true;
+    sl.n = n;
+    sl.ticket = s->next_ticket;
+    *ticket = s->next_ticket++;
+    return DFK_OK;
+  } catch (...) {
+    return oom(h);
+  }
+}
+
+DfkStatus dfk_sfm_stream_wait(DfkHandle h, DfkSfmStream* s, uint64_t ticket, float* records_host)
+{
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!s || !records_host) return fail(h, DFK_ERR_INVALID_ARG, "[SfmStream] null argument");
+    DfkSfmStream::Slot& sl = s->slots[ticket % (uint64_t)s->depth];
+    if (!sl.busy || sl.ticket != ticket || ticket != s->next_wait)
+      return fail(h, DFK_ERR_INVALID_ARG, "[SfmStream] tickets must be waited for once, in submission order");
+    DeviceGuard guard(h->device);
+    DFK_CUDA(h, cudaEventSynchronize(sl.done), "[SfmStream] kernel launch failed");
+    memcpy(records_host, sl.rec_host, (size_t)DFK_SFM_RECORD_FLOATS(s->code_size) * sl.n * sizeof(float));
+    sl.busy = false;
+    s->next_wait += 1;
+    return DFK_OK;
+  } catch (...) {
+    return oom(h);
+  }
+}
+
+DfkStatus dfk_depth_run_step(DfkHandle h, const float* code, int code_size, const DfkImage* target_dpt,
+                             const DfkImage* prx_orig, const DfkImage* prx_jac, float* JtJ, float* Jtr, float* residual,
+                             uint64_t* inliers)
+{
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!code || !target_dpt || !prx_orig || !prx_jac || !JtJ || !Jtr || !residual || !inliers)
+      return fail(h, DFK_ERR_INVALID_ARG, "[DepthAligner::RunStep] null argument");
+    // CHECK_EQ(codesize, CS) (cu_depthaligner.cpp:90-91): the code size must be one this build instantiates
+    if (!(code_size == 8 || code_size == 16 || code_size == 32 || code_size == 64 || code_size == 128))
+      return fail(h, DFK_ERR_UNSUPPORTED,
+                  "DepthAligner used with a different code size than it was compiled for: " + std::to_string(code_size));
+    const uint32_t W = target_dpt->width, H = target_dpt->height;
+    if (W == 0 || H == 0 || !img_ok(target_dpt, W, H, 1) || !img_ok(prx_orig, W, H, 1) || !img_ok(prx_jac, W, H, code_size))
+      return fail(h, DFK_ERR_INVALID_ARG, "[DepthAligner::RunStep] inconsistent image views");
+    DeviceGuard guard(h->device);
+    const int area = (int)(W * H);
+    const int blocks = std::max(1, std::min(2 * h->num_sms, (area + 63) / 64));
+    const size_t NH = (size_t)code_size * (code_size + 1) / 2, REC = NH + code_size + 2;
+    DFK_CUDA(h, ensure(&h->partials_dev, &h->partials_cap, (size_t)blocks * depth_partial_floats(code_size)),
+             "[DepthAligner::RunStep] scratch allocation failed");
+    DFK_CUDA(h, ensure(&h->records_dev, &h->records_cap, REC), "[DepthAligner::RunStep] scratch allocation failed");
+    if (h->records_host_cap < REC) {
+      if (h->records_host) cudaFreeHost(h->records_host);
+      h->records_host = nullptr;
+      h->records_host_cap = 0;
+      DFK_CUDA(h, cudaMallocHost((void**)&h->records_host, REC * sizeof(float)), "[DepthAligner::RunStep] pinned allocation failed");
+      h->records_host_cap = REC;
+    }
+    DFK_CUDA(h, cudaMemcpyAsync(h->code_dev, code, sizeof(float) * code_size, cudaMemcpyHostToDevice, h->stream),
+             "[DepthAligner::RunStep] code upload failed");
+    DFK_CUDA(h, launch_depth_step(h->code_dev, code_size, (int)W, (int)H, view_of(target_dpt), view_of(prx_orig),
+                                  view_of(prx_jac), h->params.sfmparams.avg_dpt, h->partials_dev, h->counter, h->records_dev,
+                                  blocks, h->stream),
+             "[DepthAligner::RunStep] kernel launch failed");
+    h->launches += 1;
+    DFK_CUDA(h, cudaMemcpyAsync(h->records_host, h->records_dev, REC * sizeof(float), cudaMemcpyDeviceToHost, h->stream),
+             "[DepthAligner::RunStep] kernel launch failed");
+    DFK_CUDA(h, cudaStreamSynchronize(h->stream), "[DepthAligner::RunStep] kernel launch failed");
+    memcpy(JtJ, h->records_host, sizeof(float) * NH);
+    memcpy(Jtr, h->records_host + NH, sizeof(float) * code_size);
+    *residual = h->records_host[NH + code_size];
+    uint32_t bits;
+    memcpy(&bits, &h->records_host[NH + code_size + 1], 4);
+    *inliers = bits;
     return DFK_OK;
   } catch (...) {
     return oom(h);

@@ -5,6 +5,12 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#if defined(__CUDA_ARCH__)
+#define DFK_UNROLL _Pragma("unroll")
+#else
+#define DFK_UNROLL
+#endif
+
 namespace dfk {
 
 // ------------------------------------------------------------------------------ on-device Gauss-Newton update
@@ -15,40 +21,76 @@ namespace dfk {
 // the pose where the reference moves it, and an all-zero system (no inliers) leaves it alone.
 __host__ __device__ inline void ldlt6_solve(float A[6][6] /* full symmetric, destroyed */, const float b[6], float x[6])
 {
+  // Every array index below is a compile-time constant after unrolling (the pivot swap is a chain of predicated static
+  // swaps), so the 6x6 system lives in registers.  (A version with run-time row / column indices gave wrong updates
+  // inside se3_step_kernel while the same code was right in a stand-alone kernel: tools/ldlt_probe.cu.)
   int perm[6];
+DFK_UNROLL
   for (int i = 0; i < 6; ++i) perm[i] = i;
+DFK_UNROLL
   for (int k = 0; k < 6; ++k) {
     int p = k;
     float best = fabsf(A[k][k]);
+DFK_UNROLL
     for (int i = k + 1; i < 6; ++i)
       if (fabsf(A[i][i]) > best) {
         best = fabsf(A[i][i]);
         p = i;
       }
-    if (p != k) {  // P A P^T: rows k <-> p (the finished L columns and the trailing block), then columns k <-> p
-      for (int c = 0; c < 6; ++c) { const float t = A[k][c]; A[k][c] = A[p][c]; A[p][c] = t; }
-      for (int r = 0; r < 6; ++r) { const float t = A[r][k]; A[r][k] = A[r][p]; A[r][p] = t; }
-      const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+    // P A P^T: rows k <-> p (the finished L columns and the trailing block), then columns k <-> p
+DFK_UNROLL
+    for (int i = k + 1; i < 6; ++i) {
+      if (p == i) {
+DFK_UNROLL
+        for (int c = 0; c < 6; ++c) { const float t = A[k][c]; A[k][c] = A[i][c]; A[i][c] = t; }
+DFK_UNROLL
+        for (int r = 0; r < 6; ++r) { const float t = A[r][k]; A[r][k] = A[r][i]; A[r][i] = t; }
+        const int t = perm[k]; perm[k] = perm[i]; perm[i] = t;
+      }
     }
     const float d = A[k][k];
     if (fabsf(d) > 1.17549435e-38f) {
       float col[6];
+DFK_UNROLL
       for (int i = k + 1; i < 6; ++i) col[i] = A[i][k] / d;  // L_ik
+DFK_UNROLL
       for (int i = k + 1; i < 6; ++i)
+DFK_UNROLL
         for (int j = k + 1; j < 6; ++j) A[i][j] -= col[i] * A[j][k];  // A[j][k] still holds L_jk * d
+DFK_UNROLL
       for (int i = k + 1; i < 6; ++i) A[i][k] = col[i];
     } else {
+DFK_UNROLL
       for (int i = k + 1; i < 6; ++i) A[i][k] = 0.0f;
     }
   }
   float y[6];
-  for (int i = 0; i < 6; ++i) y[i] = b[perm[i]];
+DFK_UNROLL
+  for (int i = 0; i < 6; ++i) {
+    float v = 0.0f;
+DFK_UNROLL
+    for (int j = 0; j < 6; ++j)
+      if (perm[i] == j) v = b[j];
+    y[i] = v;
+  }
+DFK_UNROLL
   for (int i = 0; i < 6; ++i)
+DFK_UNROLL
     for (int k = 0; k < i; ++k) y[i] -= A[i][k] * y[k];
+DFK_UNROLL
   for (int i = 0; i < 6; ++i) y[i] = fabsf(A[i][i]) > 1.17549435e-38f ? y[i] / A[i][i] : 0.0f;
+DFK_UNROLL
   for (int i = 5; i >= 0; --i)
+DFK_UNROLL
     for (int k = i + 1; k < 6; ++k) y[i] -= A[k][i] * y[k];
-  for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+DFK_UNROLL
+  for (int j = 0; j < 6; ++j) {
+    float v = 0.0f;
+DFK_UNROLL
+    for (int i = 0; i < 6; ++i)
+      if (perm[i] == j) v = y[i];
+    x[j] = v;
+  }
 }
 
 __host__ __device__ inline bool gn_update_pose(const float* __restrict__ sys /*21 JtJ packed upper, 6 Jtr*/, float* pose /*qx qy qz qw tx ty tz*/)

@@ -154,6 +154,12 @@ struct WindowDev {
 };
 cudaError_t launch_window_assemble(const WindowDev& w, const float* records_dev, float* out_dev, cudaStream_t stream);
 
+// dfk_depth.cu : DepthAligner::RunStep
+size_t depth_partial_floats(int code_size);
+cudaError_t launch_depth_step(const float* code_dev, int code_size, int width, int height, View tgt, View prx_orig,
+                              View jac, float avg_dpt, float* scratch /*blocks * depth_partial_floats*/,
+                              unsigned int* counter, float* out_dev /*C(C+1)/2 + C + 2*/, int blocks, cudaStream_t s);
+
 constexpr int kSimpleMaxBlocks = 1024;
 constexpr int kSimpleScratchFloats = kSimpleMaxBlocks * 32;
 

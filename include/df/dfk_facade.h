@@ -321,6 +321,41 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------
+// df::DepthAligner<Scalar, CS>  (cu_depthaligner.h:38-54)
+// ---------------------------------------------------------------------------------------------
+template <typename Scalar, int CS>
+class DepthAligner
+{
+  static_assert(sizeof(Scalar) == sizeof(float), "only float is instantiated (cu_depthaligner.cpp:118)");
+
+public:
+  typedef std::shared_ptr<DepthAligner<Scalar, CS>> Ptr;
+  typedef JTJJrReductionItem<Scalar, CS> ReductionItem;
+
+  DepthAligner() : h_(detail::MakeHandle()) {}
+  virtual ~DepthAligner() {}
+
+  // cu_depthaligner.cpp:83-113; CodeT = Eigen::Matrix<Scalar,CS,1> (anything with data()), ImageBuffer = vc::Image2DView
+  template <typename CodeT, typename ImageBuffer>
+  ReductionItem RunStep(const CodeT& code, const ImageBuffer& target_dpt, const ImageBuffer& prx_orig,
+                        const ImageBuffer& prx_jac)
+  {
+    const DfkImage t = detail::View(target_dpt, 1), p = detail::View(prx_orig, 1), j = detail::View(prx_jac, CS);
+    ReductionItem r;
+    uint64_t inl = 0;
+    detail::Check(h_.get(), dfk_depth_run_step(h_.get(), code.data(), CS, &t, &p, &j, r.JtJ.coeff().data(), r.Jtr.data(),
+                                               &r.residual, &inl));
+    r.inliers = static_cast<std::size_t>(inl);
+    return r;
+  }
+  DfkHandle handle() const { return h_.get(); }
+  void SetStream(void* stream) { detail::Check(h_.get(), dfk_set_stream(h_.get(), stream)); }
+
+private:
+  detail::HandlePtr h_;
+};
+
+// ---------------------------------------------------------------------------------------------
 // df::SE3Aligner<Scalar>  (cu_se3aligner.h:38-86)
 // ---------------------------------------------------------------------------------------------
 template <typename Scalar>

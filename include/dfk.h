@@ -184,6 +184,26 @@ DfkStatus dfk_sfm_run_step_batch(DfkHandle h, const DfkSfmWorkItem* items, int n
 DfkStatus dfk_sfm_run_step_batch_host(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size,
                                       float* records_host);
 
+/* ------------------------------------------------------------------ streaming evaluation from HOST memory
+ *
+ * The reference's inputs live in host/device mirrored pyramids that are uploaded lazily, one synchronous copy at a
+ * time, on first GPU use (sources/cuda/synced_pyramid.h:118-126,178-198).  This is the same hand-over as ONE pipelined
+ * call: dfk_sfm_stream_submit takes work items whose image views point at HOST memory (pinned for full speed), uploads
+ * them on a copy stream into one of `depth` device slots, evaluates them (dfk_sfm_run_step_batch) on the handle's stream
+ * as soon as the upload has landed and sends the result records back -- all asynchronous, so the upload of submission
+ * k+1 overlaps the evaluation of submission k.  dfk_sfm_stream_wait blocks until the records of a ticket are in host
+ * memory.  Tickets must be waited for in order; at most `depth` submissions may be outstanding.
+ * valid0 of a streamed item is device scratch (the mask is neither uploaded nor returned); with the fused depth decode
+ * (code != NULL) prx_orig is uploaded instead of dpt0 and the decoded depth stays on the device.
+ */
+typedef struct DfkSfmStream DfkSfmStream;
+DfkStatus dfk_sfm_stream_create(DfkHandle h, int code_size, int max_items, size_t max_bytes_per_submit, int depth,
+                                DfkSfmStream** out);
+DfkStatus dfk_sfm_stream_destroy(DfkHandle h, DfkSfmStream* s);
+DfkStatus dfk_sfm_stream_submit(DfkHandle h, DfkSfmStream* s, const DfkSfmWorkItem* host_items, int n,
+                                uint64_t* ticket);
+DfkStatus dfk_sfm_stream_wait(DfkHandle h, DfkSfmStream* s, uint64_t ticket, float* records_host);
+
 /* ------------------------------------------------------------------ keyframe window (block-sparse normal equations)
  *
  * What the factor graph does with the RunStep results of a window of keyframes: every (pair, level) result is one
@@ -261,6 +281,16 @@ DfkStatus dfk_se3_track(DfkHandle h, float pose_ck[7], const DfkTrackLevel* leve
 DfkStatus dfk_se3_warp(DfkHandle h, const float se3[7], const DfkCamera* cam,
                        const DfkImage* img0, const DfkImage* img1, const DfkImage* dpt0,
                        const DfkImage* img2, float* residual, uint64_t* inliers);
+
+/* ------------------------------------------------------------------ DepthAligner */
+
+/* DepthAligner<float,CS>::RunStep (sources/cuda/cu_depthaligner.h:46-49, cu_depthaligner.cpp:32-113): aligns the depth
+ * decoded from `code` (HOST, code_size floats) to target_dpt; every pixel counts.  JtJ[CS(CS+1)/2] packed upper,
+ * Jtr[CS], residual = sum diff^2, inliers = W*H.  The reference hard-codes avg_dpt = 2 in this kernel (:44); here it
+ * is the handle's DenseSfmParams::avg_dpt (same default).  Synchronous. */
+DfkStatus dfk_depth_run_step(DfkHandle h, const float* code, int code_size, const DfkImage* target_dpt,
+                             const DfkImage* prx_orig, const DfkImage* prx_jac,
+                             float* JtJ, float* Jtr, float* residual, uint64_t* inliers);
 
 /* ------------------------------------------------------------------ cu_image_proc free functions */
 

@@ -165,6 +165,15 @@ void dfko_update_depth_f(const float* code, int code_size, int width, int height
                          const float* prx_orig, size_t prx_pitch, const float* prx_jac, size_t jac_pitch,
                          float avg_dpt, float* dpt_out, size_t dpt_pitch);
 
+/* ---- DepthAligner::RunStep (cu_depthaligner.cpp:32-113): every pixel counts; JtJ packed upper C(C+1)/2, Jtr C.
+ * avg_dpt is hard-coded to 2 in the reference kernel (:44); a parameter here. */
+void dfko_depth_run_step_f(const float* code, int code_size, int width, int height, const float* tgt, size_t tgt_pitch,
+                           const float* prx_orig, size_t prx_pitch, const float* prx_jac, size_t jac_pitch, float avg_dpt,
+                           float* JtJ, float* Jtr, float* residual, uint64_t* inliers);
+void dfko_depth_run_step_d(const float* code, int code_size, int width, int height, const float* tgt, size_t tgt_pitch,
+                           const float* prx_orig, size_t prx_pitch, const float* prx_jac, size_t jac_pitch, float avg_dpt,
+                           double* JtJ, double* Jtr, double* residual, uint64_t* inliers);
+
 /* ---- pyramid construction (cu_image_proc.cpp:57-92, 134-164) and SquaredError (:190-242) */
 void dfko_sobel_gradients_f(int width, int height, const float* img, size_t img_pitch,
                             float* grad /* (gx,gy) interleaved */, size_t grad_pitch);

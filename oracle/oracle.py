@@ -282,6 +282,24 @@ def update_depth(code, prx_orig, prx_jac, avg_dpt=2.0):
     return out
 
 
+def depth_run_step(code, target_dpt, prx_orig, prx_jac, avg_dpt=2.0, *, precision="f32") -> StepResult:
+    """DepthAligner::RunStep on the CPU (cu_depthaligner.cpp:32-113)."""
+    code = np.ascontiguousarray(code, dtype=np.float32)
+    tgt, prx_orig, prx_jac = _f32(target_dpt), _f32(prx_orig), _f32(prx_jac)
+    H, W = tgt.shape
+    Cs = code.shape[0]
+    inl = C.c_uint64(0)
+    args = (_ptr(code), C.c_int(Cs), C.c_int(W), C.c_int(H), _ptr(tgt), _pitch(tgt), _ptr(prx_orig), _pitch(prx_orig),
+            _ptr(prx_jac), _pitch(prx_jac), C.c_float(avg_dpt))
+    if precision == "f64":
+        JtJ, Jtr, res = np.zeros(Cs * (Cs + 1) // 2), np.zeros(Cs), C.c_double(0)
+        lib().dfko_depth_run_step_d(*args, _ptr(JtJ, C.c_double), _ptr(Jtr, C.c_double), C.byref(res), C.byref(inl))
+    else:
+        JtJ, Jtr, res = np.zeros(Cs * (Cs + 1) // 2, dtype=np.float32), np.zeros(Cs, dtype=np.float32), C.c_float(0)
+        lib().dfko_depth_run_step_f(*args, _ptr(JtJ), _ptr(Jtr), C.byref(res), C.byref(inl))
+    return StepResult(JtJ, Jtr, float(res.value), int(inl.value))
+
+
 def sobel_gradients(img):
     img = _f32(img)
     H, W = img.shape

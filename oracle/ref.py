@@ -126,6 +126,22 @@ def se3_run_step(se3, cam, img0, img1, dpt0, grad1, huber_delta=0.1) -> StepResu
     return StepResult(JtJ, Jtr, float(res.value), int(inl.value))
 
 
+def depth_run_step(code, target_dpt, prx_orig, prx_jac, avg_dpt=2.0) -> StepResult:
+    code = np.ascontiguousarray(code, dtype=np.float32)
+    tgt, prx_orig, prx_jac = _f32(target_dpt), _f32(prx_orig), _f32(prx_jac)
+    H, W = tgt.shape
+    Cs = code.shape[0]
+    inl, res = C.c_uint64(0), C.c_float(0)
+    JtJ, Jtr = np.zeros(Cs * (Cs + 1) // 2, dtype=np.float32), np.zeros(Cs, dtype=np.float32)
+    fn = lib().dfkr_depth_run_step_f
+    fn.restype = C.c_int
+    rc = fn(_ptr(code), C.c_int(Cs), C.c_int(W), C.c_int(H), _ptr(tgt), _pitch(tgt), _ptr(prx_orig), _pitch(prx_orig),
+            _ptr(prx_jac), _pitch(prx_jac), C.c_float(avg_dpt), _ptr(JtJ), _ptr(Jtr), C.byref(res), C.byref(inl))
+    if rc != 0:
+        raise ValueError("code size not instantiated")
+    return StepResult(JtJ, Jtr, float(res.value), int(inl.value))
+
+
 def update_depth(code, prx_orig, prx_jac, avg_dpt=2.0):
     code = np.ascontiguousarray(code, dtype=np.float32)
     prx_orig, prx_jac = _f32(prx_orig), _f32(prx_jac)

@@ -124,6 +124,38 @@ void update_depth(const float* code_in, int width, int height, const float* prx_
     }
 }
 
+// Body of kernel_depthaligner_run_step (cuda/cu_depthaligner.cpp:46-65) run for every pixel once, row-major: the kernel
+// is a __device__ lambda inside a .cpp compiled as CUDA, so the statements are repeated here around the reference's own
+// df::DepthFromCode / df::DepthJacobianPrx (warping.h) and its reduction item.  avg_dpt = 2 is hard-coded there (:44).
+template <int CS>
+void depth_run_step(const float* code_in, int width, int height, const float* tgt, size_t tgt_pitch, const float* prx_orig,
+                    size_t prx_pitch, const float* jac, size_t jac_pitch, float avg_dpt, float* JtJ, float* Jtr,
+                    float* residual, uint64_t* inliers)
+{
+  using Item = df::JTJJrReductionItem<float, CS>;
+  Eigen::Matrix<float, CS, 1> code;
+  for (int k = 0; k < CS; ++k) code(k) = code_in[k];
+  const ImgView vtgt = view(tgt, width, height, tgt_pitch), vprx = view(prx_orig, width, height, prx_pitch);
+  const ImgView vjac(const_cast<float*>(jac), (size_t)width * CS, (size_t)height, jac_pitch * sizeof(float));
+  Item sum;
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x) {
+      Eigen::Map<const Eigen::Matrix<float, 1, CS>> tmp(&vjac(x * CS, y));
+      const Eigen::Matrix<float, 1, CS> prx_J_cde(tmp);
+      float dpt = df::DepthFromCode(code, prx_J_cde, vprx(x, y), avg_dpt);
+      float diff = vtgt(x, y) - dpt;
+      Eigen::Matrix<float, 1, CS> J = -2 * abs(diff) * df::DepthJacobianPrx(dpt, avg_dpt) * prx_J_cde;
+      sum.inliers += 1;
+      sum.residual += diff * diff;
+      sum.Jtr += J.transpose() * diff;
+      sum.JtJ += typename Item::HessianType(J.transpose());
+    }
+  for (int k = 0; k < CS * (CS + 1) / 2; ++k) JtJ[k] = sum.JtJ.coeff()(k);
+  for (int k = 0; k < CS; ++k) Jtr[k] = sum.Jtr(k);
+  *residual = sum.residual;
+  *inliers = sum.inliers;
+}
+
 }  // namespace
 
 extern "C" {
@@ -296,6 +328,26 @@ double dfkr_sfm_throughput_f(int nthreads, int evals_per_thread, const float pos
   const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (rec_out) std::memcpy(rec_out, recs.data(), sizeof(float) * REC);
   return dt;
+}
+
+// DepthAligner::RunStep's math (cu_depthaligner.cpp:32-71)
+int dfkr_depth_run_step_f(const float* code, int code_size, int width, int height, const float* tgt, size_t tgt_pitch,
+                          const float* prx_orig, size_t prx_pitch, const float* prx_jac, size_t jac_pitch, float avg_dpt,
+                          float* JtJ, float* Jtr, float* residual, uint64_t* inliers)
+{
+#define DFKR_DCASE(CS)                                                                                                   \
+  case CS:                                                                                                               \
+    depth_run_step<CS>(code, width, height, tgt, tgt_pitch, prx_orig, prx_pitch, prx_jac, jac_pitch, avg_dpt, JtJ, Jtr,  \
+                       residual, inliers);                                                                              \
+    return 0;
+  switch (code_size) {
+    DFKR_DCASE(8)
+    DFKR_DCASE(16)
+    DFKR_DCASE(32)
+    DFKR_DCASE(64)
+    default: return -1;
+  }
+#undef DFKR_DCASE
 }
 
 // UpdateDepth's math (cu_image_proc.cpp:248-264, warping.h:52-69)

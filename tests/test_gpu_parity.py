@@ -490,3 +490,80 @@ def test_window_assembly_on_device_matches_host_mirror():
         assert np.abs(Hd - Hr).max() <= 2e-6 * np.abs(Hr).max() and np.abs(gd - gr).max() <= 2e-6 * np.abs(gr).max()
         assert abs(f - fr) <= 1e-5 * abs(fr) and ninl == float(inl.sum())
         assert np.allclose(Hd, Hd.T)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,cs", [(160, 120, 32), (80, 60, 8), (97, 33, 16), (64, 48, 128)])
+def test_depth_aligner_run_step_matches_oracle(oracle, w, h, cs):
+    """DepthAligner::RunStep (cu_depthaligner.cpp:32-113) vs the CPU oracle (fp64): every pixel counts."""
+    import torch
+    from deepfactors_b200.aligners import DepthAligner
+    L = synth.make_level(w, h, cs, seed=8)
+    code = (np.random.default_rng(3).standard_normal(cs) * 0.3).astype(np.float32)
+    tgt = (L.dpt0 * np.float32(1.05) + np.float32(0.02)).astype(np.float32)
+    da = DepthAligner(cs)
+    g = da.RunStep(code, pitched(torch, tgt, 3), pitched(torch, L.prx_orig), pitched(torch, L.prx_jac, 4))
+    o = oracle.depth_run_step(code, tgt, L.prx_orig, L.prx_jac, 2.0, precision="f64")
+    assert g.inliers == o.inliers == w * h
+    assert np.abs(g.JtJ - o.JtJ).max() <= 2e-5 * np.abs(o.JtJ).max()
+    assert np.abs(g.Jtr - o.Jtr).max() <= 1e-4 * np.abs(o.Jtr).max()
+    assert abs(g.residual - o.residual) <= 1e-5 * abs(o.residual)
+    g2 = da.RunStep(code, pitched(torch, tgt, 3), pitched(torch, L.prx_orig), pitched(torch, L.prx_jac, 4))
+    assert np.array_equal(g.JtJ, g2.JtJ)  # fixed summation order
+
+
+@pytest.mark.gpu
+def test_streaming_from_host_matches_device_resident_batch():
+    """dfk_sfm_stream_submit / _wait (host image views, pipelined upload) returns the records of the device-resident
+    batch, bit for bit, for several submissions in flight."""
+    import ctypes as C
+    import torch
+    from deepfactors_b200 import _lib
+    from deepfactors_b200._lib import DfkCamera, DfkImage, DfkSfmWorkItem
+    from deepfactors_b200.aligners import SfmAligner
+    cs = 32
+    al = SfmAligner(cs)
+    lib = _lib.lib()
+    rec = _lib.record_floats(cs)
+    pairs = [synth.make_pair(160, 120, cs, 2, seed=60 + k, code_sigma=0.2) for k in range(4)]
+    want = []
+    for pr in pairs:
+        items = []
+        for L in pr.levels:
+            d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in dict(
+                img0=L.img0, img1=L.img1, dpt0=L.dpt0, prx0_jac=L.prx_jac, grad1=L.grad1).items()}
+            items.append(dict(pose0=pr.pose0, pose1=pr.pose1, cam=L.cam, valid0=torch.zeros_like(d["img0"]), **d))
+        want.append(al.RunStepBatch(al.make_work_items(items)).cpu().numpy())
+    keep, arrs = [], []
+    for pr in pairs:
+        arr = (DfkSfmWorkItem * 2)()
+        for l, L in enumerate(pr.levels):
+            t = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in dict(
+                img0=L.img0, img1=L.img1, dpt0=L.dpt0, prx0_jac=L.prx_jac, grad1=L.grad1).items()}
+            keep.append(t)
+            w = arr[l]
+            w.pose0 = (C.c_float * 7)(*np.asarray(pr.pose0, dtype=np.float32).tolist())
+            w.pose1 = (C.c_float * 7)(*np.asarray(pr.pose1, dtype=np.float32).tolist())
+            w.cam = DfkCamera(L.cam.fx, L.cam.fy, L.cam.u0, L.cam.v0, L.cam.width, L.cam.height)
+            im = lambda x: DfkImage(C.c_void_p(x.data_ptr()), x.stride(0) * 4, x.shape[1], x.shape[0])
+            w.img0, w.img1, w.dpt0, w.prx0_jac, w.grad1 = im(t["img0"]), im(t["img1"]), im(t["dpt0"]), im(t["prx0_jac"]), im(t["grad1"])
+        arrs.append(arr)
+    al._hd.use_torch_stream()
+    st = C.c_void_p()
+    _lib.check(al.handle, lib.dfk_sfm_stream_create(al.handle, cs, 2, 1 << 16, 3, C.byref(st)))  # small hint: slots must grow
+    tk = C.c_uint64(0)
+    for arr in arrs[:3]:
+        _lib.check(al.handle, lib.dfk_sfm_stream_submit(al.handle, st, arr, 2, C.byref(tk)))
+    # a fourth submission with three outstanding is refused, waiting out of order too
+    assert lib.dfk_sfm_stream_submit(al.handle, st, arrs[3], 2, C.byref(tk)) == _lib.DFK_ERR_INVALID_ARG
+    out = np.zeros((2, rec), dtype=np.float32)
+    op = out.ctypes.data_as(C.POINTER(C.c_float))
+    assert lib.dfk_sfm_stream_wait(al.handle, st, C.c_uint64(1), op) == _lib.DFK_ERR_INVALID_ARG
+    for k in range(3):
+        _lib.check(al.handle, lib.dfk_sfm_stream_wait(al.handle, st, C.c_uint64(k), op))
+        assert np.array_equal(out, want[k]), f"submission {k}"
+        if k == 0:
+            _lib.check(al.handle, lib.dfk_sfm_stream_submit(al.handle, st, arrs[3], 2, C.byref(tk)))
+    _lib.check(al.handle, lib.dfk_sfm_stream_wait(al.handle, st, C.c_uint64(3), op))
+    assert np.array_equal(out, want[3])
+    lib.dfk_sfm_stream_destroy(al.handle, st)

@@ -145,3 +145,20 @@ def test_update_depth_oracle_equals_reference_headers(oracle):
     d_r = ref.update_depth(code, L.prx_orig, L.prx_jac, 2.0)
     # the 1xC * Cx1 product is summed left to right in both
     assert np.abs(d_o - d_r).max() <= 1e-6 * np.abs(d_r).max()
+
+
+@pytest.mark.parametrize("cs", [8, 32])
+def test_depth_aligner_oracle_equals_reference_headers(oracle, cs):
+    # cu_depthaligner.cpp:46-65 around the reference's own DepthFromCode / DepthJacobianPrx
+    L = synth.make_level(80, 60, cs, seed=6)
+    code = (np.random.default_rng(2).standard_normal(cs) * 0.3).astype(np.float32)
+    tgt = (L.dpt0 * np.float32(1.05) + np.float32(0.02)).astype(np.float32)
+    o = oracle.depth_run_step(code, tgt, L.prx_orig, L.prx_jac, 2.0, precision="f32")
+    r = ref.depth_run_step(code, tgt, L.prx_orig, L.prx_jac, 2.0)
+    assert o.inliers == r.inliers == 80 * 60
+    assert _rel(o.JtJ, r.JtJ) < 2e-5 and _rel(o.Jtr, r.Jtr) < 2e-5
+    assert abs(o.residual - r.residual) <= 2e-5 * abs(r.residual)
+    # analytic gradient vs finite differences of the residual energy: d(sum diff^2)/dcode = 2 sum diff * ddiff/dcode and
+    # J = -2|diff| dDpt/dPrx jc, so  Jtr_k = sum J_k diff  ==  sign-weighted; check through the energy at zero Huber:
+    o64 = oracle.depth_run_step(code, tgt, L.prx_orig, L.prx_jac, 2.0, precision="f64")
+    assert _rel(r.JtJ, o64.JtJ) < 2e-4

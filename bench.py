@@ -478,6 +478,11 @@ def main():
         if q > 0:
             d["prx0_jac"] = torch.roll(d["prx0_jac"], shifts=(3 * q, 5 * q), dims=(0, 1)).contiguous()
             d["img0"] = (d["img0"] * (1.0 - 0.01 * (q % 50))).contiguous()
+            # every variation owns ALL of its buffers (same contents for img1 / grad1 / dpt0, different memory): pairs that
+            # shared them would turn the bilinear gathers of 7 of 8 pairs into L2 hits (measured: -13 % kernel time)
+            for k in ("img1", "grad1", "dpt0", "prx_orig"):
+                if k in d:
+                    d[k] = d[k].clone()
         d["valid0"] = torch.zeros_like(d["img0"])
         return d
 
@@ -710,7 +715,7 @@ def main():
         bytes_per_eval = PIXELS * bytes_per_px
         bytes_per_launch = P * bytes_per_eval
         traffic = None  # dram__bytes_read+write of one step-kernel launch, from the committed ncu --set full capture
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if os.path.exists(tpath) and args.config == "pair8" and P == 8 and args.gram in ("auto", "tf32x3") and not args.fused_depth:
             traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
         kern_avg_ms = kern_ms / max(kern_n, 1)

@@ -259,6 +259,30 @@ class SfmAligner:
         return [JTJJrReductionItem.from_record(r[i], self.CS) for i in range(r.shape[0])]
 
 
+# ------------------------------------------------------------------------------------------- sparse keypoint factor
+def ReprojectionLinearize(aligner, pose0, pose1, code0, cam, prx_orig, prx_jac, query_xy, train_xy, cauchy_delta: float,
+                          sigma: float):
+    """ReprojectionFactor::linearize (sources/core/gtsam/reprojection_factor.cpp:157-269) with the rows gathered on the
+    device: prx_orig / prx_jac are the keyframe's level-0 DEVICE buffers, query_xy / train_xy the matched keypoints [M, 2]
+    (host).  Returns (rows [2M, 13 + C] float32 = the blocks of the JacobianFactor [J_pose0 | J_pose1 | J_code0 | b],
+    total_err)."""
+    aligner._hd.use_torch_stream()
+    cs = aligner.CS
+    code = np.ascontiguousarray(code0, dtype=np.float32)
+    q = np.ascontiguousarray(query_xy, dtype=np.float32).reshape(-1, 2)
+    t = np.ascontiguousarray(train_xy, dtype=np.float32).reshape(-1, 2)
+    M = q.shape[0]
+    rows = np.zeros((2 * M, 13 + cs), dtype=np.float32)
+    tot = C.c_float(0)
+    FP = C.POINTER(C.c_float)
+    c, p, j = _cam(cam), _image(prx_orig), _image(prx_jac, cs)
+    check(aligner.handle, lib().dfk_reprojection_linearize(
+        aligner.handle, _pose(pose0), _pose(pose1), code.ctypes.data_as(FP), cs, C.byref(c), C.byref(p), C.byref(j), M,
+        q.ctypes.data_as(FP), t.ctypes.data_as(FP), C.c_float(cauchy_delta), C.c_float(sigma), rows.ctypes.data_as(FP),
+        C.byref(tot)))
+    return rows, float(tot.value)
+
+
 # ------------------------------------------------------------------------------------------- DepthAligner
 class DepthAligner:
     """df::DepthAligner<float, CS> (sources/cuda/cu_depthaligner.h:38-54): code-only alignment of the decoded depth to a

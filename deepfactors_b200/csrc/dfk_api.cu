@@ -38,12 +38,23 @@ struct DfkContext {
   float* track_host = nullptr;       // pinned mirror of track_dev + the last system (32)
   size_t track_host_cap = 0;
 
+  float* sparse_dev = nullptr;       // dfk_reprojection_linearize: [query | train | rows | err2]
+  size_t sparse_cap = 0;
+  float* sparse_host = nullptr;      // pinned mirror
+  size_t sparse_host_cap = 0;
   SfmItemDev* items_dev = nullptr;
   size_t items_cap = 0;
   float* partials_dev = nullptr;
   size_t partials_cap = 0;  // floats
-  float* ray_tabs_dev = nullptr;
-  size_t ray_tabs_cap = 0;  // floats
+  // normalised ray tables of the tensor-core kernel: they depend on (fx, u0, width, fy, v0, height) only, so they are
+  // built once per camera level and reused by every later call (one launch less per evaluation in steady state)
+  struct RayTab {
+    float fx, fy, u0, v0;
+    uint32_t w, h;
+    float* dev;
+  };
+  std::vector<RayTab> ray_cache;
+  bool ray_miss = false;  // build_items found a camera without a table: run the table kernel this call
   float* codes_dev = nullptr;  // fused depth decode: code_size floats per work item
   size_t codes_cap = 0;
   std::vector<float> codes_host;
@@ -283,9 +294,9 @@ cudaError_t ensure(T** ptr, size_t* cap, size_t need)
 }
 
 DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_size, int tile_px, int max_ctas,
-                      float* ray_tabs, const float* codes_dev, SfmLaunchPlan* plan)
+                      bool want_ray_tabs, const float* codes_dev, SfmLaunchPlan* plan)
 {
-  size_t ray_cursor = 0;
+  h->ray_miss = false;
   const DfkDenseSfmParams& sp = h->params.sfmparams;
   h->items_host.resize(n);
   uint32_t tile_cursor = 0;
@@ -334,8 +345,26 @@ DfkStatus build_items(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_
     }
     d.width = W; d.height = H; d.num_pixels = W * H;
     d.num_tiles = (d.num_pixels + tile_px - 1) / tile_px;
-    d.ray_tab = ray_tabs ? ray_tabs + ray_cursor : nullptr;
-    ray_cursor += (size_t)W + H;
+    d.ray_tab = nullptr;
+    if (want_ray_tabs) {
+      for (const auto& r : h->ray_cache)
+        if (r.fx == d.fx && r.fy == d.fy && r.u0 == d.u0 && r.v0 == d.v0 && r.w == W && r.h == H) {
+          d.ray_tab = r.dev;
+          break;
+        }
+      if (!d.ray_tab) {
+        if (h->ray_cache.size() >= 256) {  // a caller cycling through cameras: start over (cudaFree synchronises)
+          for (auto& r : h->ray_cache) cudaFree(r.dev);
+          h->ray_cache.clear();
+        }
+        DfkContext::RayTab r{d.fx, d.fy, d.u0, d.v0, W, H, nullptr};
+        if (cudaMalloc((void**)&r.dev, sizeof(float) * ((size_t)W + H)) != cudaSuccess)
+          return fail(h, DFK_ERR_CUDA, "[SfmAligner::RunStep] scratch allocation failed");
+        h->ray_cache.push_back(r);
+        d.ray_tab = r.dev;
+        h->ray_miss = true;
+      }
+    }
     d.tile_begin = tile_cursor;
     tile_cursor += d.num_tiles;
     d.perm_mul = perm_multiplier(d.num_tiles);
@@ -436,11 +465,6 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
                     std::to_string(code_size));
   DeviceGuard guard(h->device);
   SfmLaunchPlan plan;
-  if (tc) {
-    size_t ray_floats = 0;
-    for (int i = 0; i < n; ++i) ray_floats += (size_t)items[i].img0.width + items[i].img0.height;
-    DFK_CUDA(h, ensure(&h->ray_tabs_dev, &h->ray_tabs_cap, ray_floats), "[SfmAligner::RunStep] scratch allocation failed");
-  }
   const int tile_px = tc ? kTcTilePixels : (wide ? sfm_wide_tile_pixels(code_size) : kTilePixels);
   bool any_fused = false;
   for (int i = 0; i < n; ++i) any_fused = any_fused || items[i].code != nullptr;
@@ -450,7 +474,7 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
   }
   const int ctas_per_sm = tc ? 2 : (wide ? 1 : sfm_fp32_ctas_per_sm(code_size));
   DfkStatus st = build_items(h, items, n, code_size, tile_px, ctas_per_sm * h->num_sms,
-                             tc ? h->ray_tabs_dev : nullptr, h->codes_dev, &plan);
+                             tc, h->codes_dev, &plan);
   if (st != DFK_OK) return st;
   if (any_fused)
     DFK_CUDA(h, cudaMemcpyAsync(h->codes_dev, h->codes_host.data(), sizeof(float) * (size_t)n * code_size,
@@ -469,9 +493,9 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     if (ps != DFK_OK) return ps;
   }
   if (tc) {
-    DFK_CUDA(h, launch_sfm_tc(h->items_dev, plan, h->ray_tabs_dev, h->partials_dev, h->stream, ev0, ev1),
+    DFK_CUDA(h, launch_sfm_tc(h->items_dev, plan, h->ray_miss, h->partials_dev, h->stream, ev0, ev1),
              "[SfmAligner::RunStep] kernel launch failed");
-    h->launches += 1;  // ray-table kernel
+    if (h->ray_miss) h->launches += 1;  // ray-table kernel
   } else if (wide) {
     DFK_CUDA(h, launch_sfm_wide(code_size, h->items_dev, plan, h->partials_dev, h->stream, ev0, ev1),
              "[SfmAligner::RunStep] kernel launch failed");
@@ -558,7 +582,8 @@ DfkStatus dfk_destroy(DfkHandle h)
     cudaFree(h->track_dev);
     cudaFree(h->codes_dev);
     if (h->track_host) cudaFreeHost(h->track_host);
-    cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev); cudaFree(h->ray_tabs_dev);
+    cudaFree(h->items_dev); cudaFree(h->partials_dev); cudaFree(h->records_dev);
+    for (auto& r : h->ray_cache) cudaFree(r.dev);
     if (h->out_host) cudaFreeHost(h->out_host);
     if (h->records_host) cudaFreeHost(h->records_host);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -1383,6 +1408,70 @@ DfkStatus dfk_depth_run_step(DfkHandle h, const float* code, int code_size, cons
     uint32_t bits;
     memcpy(&bits, &h->records_host[NH + code_size + 1], 4);
     *inliers = bits;
+    return DFK_OK;
+  } catch (...) {
+    return oom(h);
+  }
+}
+
+DfkStatus dfk_reprojection_linearize(DfkHandle h, const float pose0[7], const float pose1[7], const float* code0,
+                                     int code_size, const DfkCamera* cam, const DfkImage* prx_orig, const DfkImage* prx_jac,
+                                     int num_matches, const float* query_xy, const float* train_xy, float cauchy_delta,
+                                     float sigma, float* rows, float* total_err)
+{
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!pose0 || !pose1 || !code0 || !cam || !prx_orig || !prx_jac || !query_xy || !train_xy || !rows || !total_err)
+      return fail(h, DFK_ERR_INVALID_ARG, "[ReprojectionFactor::linearize] null argument");
+    if (!(code_size == 8 || code_size == 16 || code_size == 32 || code_size == 64 || code_size == 128))
+      return fail(h, DFK_ERR_UNSUPPORTED, "[ReprojectionFactor::linearize] code size not instantiated: " + std::to_string(code_size));
+    if (num_matches <= 0 || !(sigma > 0.0f))
+      return fail(h, DFK_ERR_INVALID_ARG, "[ReprojectionFactor::linearize] no matches / non-positive sigma");
+    const uint32_t W = prx_orig->width, H = prx_orig->height;
+    if (W == 0 || H == 0 || !img_ok(prx_orig, W, H, 1) || !img_ok(prx_jac, W, H, code_size))
+      return fail(h, DFK_ERR_INVALID_ARG, "[ReprojectionFactor::linearize] inconsistent image views");
+    DeviceGuard guard(h->device);
+    const size_t M = (size_t)num_matches, RW = 13 + (size_t)code_size;
+    const size_t n_in = 4 * M, n_out = 2 * M * RW + M;
+    DFK_CUDA(h, ensure(&h->sparse_dev, &h->sparse_cap, n_in + n_out), "[ReprojectionFactor::linearize] scratch allocation failed");
+    if (h->sparse_host_cap < n_in + n_out) {
+      if (h->sparse_host) cudaFreeHost(h->sparse_host);
+      h->sparse_host = nullptr;
+      h->sparse_host_cap = 0;
+      DFK_CUDA(h, cudaMallocHost((void**)&h->sparse_host, (n_in + n_out) * sizeof(float)),
+               "[ReprojectionFactor::linearize] pinned allocation failed");
+      h->sparse_host_cap = n_in + n_out;
+    }
+    SparsePose sp;
+    float p10[7];
+    relative_pose(pose1, pose0, p10, sp.P1, sp.P0);  // RelativePose(p1, p0, pose10_J_pose1, pose10_J_pose0), :189-190
+    for (int k = 0; k < 4; ++k) sp.q[k] = p10[k];
+    for (int k = 0; k < 3; ++k) sp.t[k] = p10[4 + k];
+    quat_to_matrix(p10, sp.R);
+    sp.fx = cam->fx; sp.fy = cam->fy; sp.u0 = cam->u0; sp.v0 = cam->v0;
+    memcpy(h->sparse_host, query_xy, 2 * M * sizeof(float));
+    memcpy(h->sparse_host + 2 * M, train_xy, 2 * M * sizeof(float));
+    float* d_query = h->sparse_dev;
+    float* d_train = d_query + 2 * M;
+    float* d_rows = d_train + 2 * M;
+    float* d_err2 = d_rows + 2 * M * RW;
+    DFK_CUDA(h, cudaMemcpyAsync(h->code_dev, code0, sizeof(float) * code_size, cudaMemcpyHostToDevice, h->stream),
+             "[ReprojectionFactor::linearize] code upload failed");
+    DFK_CUDA(h, cudaMemcpyAsync(d_query, h->sparse_host, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream),
+             "[ReprojectionFactor::linearize] match upload failed");
+    DFK_CUDA(h, launch_reprojection_rows(sp, h->code_dev, code_size, view_of(prx_orig), view_of(prx_jac), (int)W, (int)H,
+                                         num_matches, d_query, d_train, cauchy_delta, sigma, h->params.sfmparams.avg_dpt,
+                                         d_rows, d_err2, h->stream),
+             "[ReprojectionFactor::linearize] kernel launch failed");
+    h->launches += 1;
+    DFK_CUDA(h, cudaMemcpyAsync(h->sparse_host + n_in, d_rows, n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream),
+             "[ReprojectionFactor::linearize] result download failed");
+    DFK_CUDA(h, cudaStreamSynchronize(h->stream), "[ReprojectionFactor::linearize] kernel launch failed");
+    memcpy(rows, h->sparse_host + n_in, 2 * M * RW * sizeof(float));
+    float tot = 0.0f;  // Scalar total_err accumulated in match order (:179,242)
+    const float* e2 = h->sparse_host + n_in + 2 * M * RW;
+    for (size_t i = 0; i < M; ++i) tot += e2[i];
+    *total_err = tot;
     return DFK_OK;
   } catch (...) {
     return oom(h);

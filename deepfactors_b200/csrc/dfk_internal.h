@@ -53,7 +53,8 @@ struct SfmItemDev {
   float* dpt_out;
   uint32_t dpt_out_pitch;
   const float* code;
-  // normalised ray tables in device scratch: xn[0..width), then yn[0..height) (tensor-core kernel)
+  // normalised ray table of the item's camera level (device memory cached by the handle): xn[0..width), then yn[0..height)
+  // (tensor-core kernel)
   const float* ray_tab;
   // relative-pose Jacobians (warping.h:120-134), row-major 6x6; used by the finalize kernel
   float P0[36];
@@ -105,7 +106,7 @@ cudaError_t launch_sfm_wide(int code_size, const SfmItemDev* items_dev, const Sf
                             cudaEvent_t ev_stop = nullptr);
 // dfk_sfm_tc.cu
 bool sfm_tc_supported(int code_size);
-cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, float* ray_tabs_dev,
+cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, bool build_ray_tables,
                           float* partials_dev, cudaStream_t stream, cudaEvent_t ev_start = nullptr,
                           cudaEvent_t ev_stop = nullptr);
 size_t sfm_partial_floats(int code_size);
@@ -159,6 +160,17 @@ size_t depth_partial_floats(int code_size);
 cudaError_t launch_depth_step(const float* code_dev, int code_size, int width, int height, View tgt, View prx_orig,
                               View jac, float avg_dpt, float* scratch /*blocks * depth_partial_floats*/,
                               unsigned int* counter, float* out_dev /*C(C+1)/2 + C + 2*/, int blocks, cudaStream_t s);
+
+// dfk_sparse.cu : ReprojectionFactor::linearize rows
+struct SparsePose {
+  float q[4], t[3], R[9];      // pose_10 = pose1^-1 * pose0
+  float P0[36], P1[36];        // pose10_J_pose0 / pose10_J_pose1, row-major 6x6
+  float fx, fy, u0, v0;
+};
+cudaError_t launch_reprojection_rows(const SparsePose& sp, const float* code_dev, int code_size, View prx_orig, View jac,
+                                     int width, int height, int num_matches, const float* query_dev, const float* train_dev,
+                                     float cauchy_delta, float sigma, float avg_dpt, float* rows_dev, float* err2_dev,
+                                     cudaStream_t s);
 
 constexpr int kSimpleMaxBlocks = 1024;
 constexpr int kSimpleScratchFloats = kSimpleMaxBlocks * 32;

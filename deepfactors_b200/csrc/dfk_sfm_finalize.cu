@@ -52,6 +52,9 @@ sfm_finalize_kernel(const SfmItemDev* __restrict__ items, const float* __restric
   __shared__ unsigned int red_inl[kFinWarps];
   __shared__ float sum[EPL * 32];
 
+  // launched with programmatic stream serialization: the launch itself (and everything above that does not read the
+  // partials) overlaps the tail of the step kernel; the partials are valid after this grid-dependency wait
+  cudaGridDependencySynchronize();
   const SfmItemDev& I = items[blockIdx.x];
   const int unit = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,9 +205,17 @@ template <int C, bool TC>
 cudaError_t launch_fin(const SfmItemDev* items_dev, int num_items, const float* partials_dev, float* records_dev,
                        cudaStream_t stream)
 {
-  dim3 grid(num_items, C + 1);
-  sfm_finalize_kernel<C, TC><<<grid, kFinWarps * 32, 0, stream>>>(items_dev, partials_dev, records_dev);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(num_items, C + 1);
+  cfg.blockDim = dim3(kFinWarps * 32);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, sfm_finalize_kernel<C, TC>, items_dev, partials_dev, records_dev);
 }
 
 }  // namespace

@@ -147,9 +147,12 @@ __device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, 
   }
 }
 
+// with_scalars: also stage img0 / dpt0 (only the fused depth decode reads them from the stage; otherwise the front-end
+// threads fetch their own pixel with two coalesced loads long before the tile lands)
 __device__ __forceinline__ void issue_tile_loads(Smem& sm, const SfmItemDev* __restrict__ items, int it, int g, int st)
 {
   const SfmItemDev& I = items[it];
+  const bool with_scalars = (I.flags & ITEM_FLAG_FUSED_DEPTH) != 0;
   const uint32_t k = (uint32_t)g - I.tile_begin;
   const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
   const uint32_t p0 = tau * TILE;
@@ -157,13 +160,15 @@ __device__ __forceinline__ void issue_tile_loads(Smem& sm, const SfmItemDev* __r
   const uint32_t W = I.width;
   uint32_t y = p0 / W;
   uint32_t x = p0 - y * W;
-  mbar_arrive_expect_tx(&sm.tma_full[st], n * (C + 2) * 4u);
+  mbar_arrive_expect_tx(&sm.tma_full[st], n * (C + (with_scalars ? 2 : 0)) * 4u);
   uint32_t slot = 0;
   while (slot < n) {
     const uint32_t seg = min(W - x, n - slot);
     bulk_g2s(&sm.jc[st][slot * C], I.jac + (size_t)y * I.jac_pitch + (size_t)x * C, seg * C * 4u, &sm.tma_full[st]);
-    bulk_g2s(&sm.img0[st][slot], I.img0 + (size_t)y * I.img0_pitch + x, seg * 4u, &sm.tma_full[st]);
-    bulk_g2s(&sm.dpt0[st][slot], I.dpt0 + (size_t)y * I.dpt0_pitch + x, seg * 4u, &sm.tma_full[st]);
+    if (with_scalars) {
+      bulk_g2s(&sm.img0[st][slot], I.img0 + (size_t)y * I.img0_pitch + x, seg * 4u, &sm.tma_full[st]);
+      bulk_g2s(&sm.dpt0[st][slot], I.dpt0 + (size_t)y * I.dpt0_pitch + x, seg * 4u, &sm.tma_full[st]);
+    }
     slot += seg;
     x = 0;
     ++y;
@@ -332,10 +337,21 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         }
         const float xn = __ldg(I.ray_tab + pxx);              // in flight while the tile lands
         const float yn = __ldg(I.ray_tab + I.width + py);
+        // The tile's code-Jacobian rows are needed only after the geometry (compaction), so a bulk-staged tile is waited
+        // for THERE: this thread's own dpt0 / img0 come straight from global memory (coalesced, issued now).  The fused
+        // depth decode reads the rows first thing and keeps the early wait.
+        const bool early = !bulk || (I.flags & ITEM_FLAG_FUSED_DEPTH) != 0;
+        float d_g = 0.0f, i0_g = 0.0f;
+        if (!early && s < n) {
+          d_g = __ldg(I.dpt0 + (size_t)py * I.dpt0_pitch + pxx);
+          i0_g = __ldg(I.img0 + (size_t)py * I.img0_pitch + pxx);
+        }
         tm.start();
         if (bulk) {
-          mbar_wait_parked(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
-          tma_phase_bits ^= (1u << st);
+          if (early) {
+            mbar_wait_parked(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
+            tma_phase_bits ^= (1u << st);
+          }
         } else {
           // stage st was last read by the operand warps of tile i-4 (stage_empty / feat_empty completed)
           coop_tile_loads(sm, I, p0, n, st, ft);
@@ -359,7 +375,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         if (s < n) {
           const uint32_t y = py, x = pxx;
 #endif
-          float d = sm.dpt0[st][s];
+          float d = early ? sm.dpt0[st][s] : d_g;
           if (I.flags & ITEM_FLAG_FUSED_DEPTH) {
             // the stage holds prx_orig: decode the depth from this pixel's code-Jacobian row (same arithmetic as
             // update_depth_kernel: chunk fma chains + xor-butterfly; register j holds chunk j ^ (lane & 7), which the
@@ -389,7 +405,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
             float a[6], c00, c02, c11, c12;
             pose_jacobian_row(w, I.fx, I.fy, gx, gy, a, c00, c02, c11, c12);
             const float e = prx_jacobian(w, I.R, d, I.avg_dpt, gx, gy, c00, c02, c11, c12);
-            const float diff = sm.img0[st][s] - i1;
+            const float diff = (early ? sm.img0[st][s] : i0_g) - i1;
             const float hw = huber_weight(diff, I.huber_delta);
             feat[0] = hw * e;
 #pragma unroll
@@ -406,6 +422,10 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         // row 32*fwarp + r becomes the r-th VALID pixel's  s * jc[0..31]  (what the operand warps feed to the
         // tensor core).  Rotated float4 order keeps reads (row = slot) and writes (row = rank) free of bank
         // conflicts; all rows are read into registers before any is overwritten (same warp => __syncwarp).
+        if (bulk && !early) {  // now the rows are needed
+          mbar_wait_parked(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
+          tma_phase_bits ^= (1u << st);
+        }
         float4 rowv[C / 4];
 #ifdef DFK_EXP_NOCOMPACT
         if (false) {
@@ -767,15 +787,19 @@ bool sfm_tc_supported(int code_size) { return code_size == 32; }
 
 size_t sfm_tc_smem_bytes() { return sizeof(Smem); }
 
-cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, float* ray_tabs_dev,
+cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, bool build_ray_tables,
                           float* partials_dev, cudaStream_t stream, cudaEvent_t ev_start, cudaEvent_t ev_stop)
 {
   const size_t smem = sizeof(Smem);
-  cudaError_t err = cudaFuncSetAttribute(sfm_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const cudaError_t attr_err =  // once per process, not once per launch
+      cudaFuncSetAttribute(sfm_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  cudaError_t err = attr_err;
   if (err != cudaSuccess) return err;
-  sfm_ray_tables_kernel<<<plan.num_items, 256, 0, stream>>>(items_dev, ray_tabs_dev);
-  err = cudaGetLastError();
-  if (err != cudaSuccess) return err;
+  if (build_ray_tables) {  // only when the work list names a camera level the handle has no table for yet
+    sfm_ray_tables_kernel<<<plan.num_items, 256, 0, stream>>>(items_dev, nullptr);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+  }
   static const int dbg = []() { const char* e = getenv("DFK_TC_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
   if (dbg) {
     unsigned long long z[16] = {0};

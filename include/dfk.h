@@ -292,6 +292,25 @@ DfkStatus dfk_depth_run_step(DfkHandle h, const float* code, int code_size, cons
                              const DfkImage* prx_orig, const DfkImage* prx_jac,
                              float* JtJ, float* Jtr, float* residual, uint64_t* inliers);
 
+/* ------------------------------------------------------------------ sparse keypoint factor */
+
+/* ReprojectionFactor::linearize (sources/core/gtsam/reprojection_factor.cpp:157-269): the Jacobian rows of a keypoint
+ * reprojection factor, gathered on the device from the keyframe's level-0 proximity / code-Jacobian buffers instead of
+ * mirroring the whole pyramid to the host (kf_->pyr_jac.GetCpuLevel(0), :193).
+ *   query_xy / train_xy   HOST, 2 floats per match: matched keypoints in the keyframe / in the frame (:183-186)
+ *   rows                  HOST out, (2 * num_matches) x (13 + code_size), row-major:
+ *                         [dErr/dPose0 (6) | dErr/dPose1 (6) | dErr/dCode0 (C) | b (1)], already multiplied by the
+ *                         Cauchy weight (m_estimators.h:43-48, parameter `cauchy_delta` = the factor's huber_delta_) and
+ *                         divided by sigma -- the blocks of gtsam::JacobianFactor(keys, Ab) (:255-268); zero rows for a
+ *                         match whose point falls behind the camera (:204-212)
+ *   total_err             out, sum of squared UNWEIGHTED reprojection errors (total_err_, :242,258)
+ * avg_dpt is hard-coded to 2 there (:171); here it is the handle's DenseSfmParams::avg_dpt.  Synchronous. */
+DfkStatus dfk_reprojection_linearize(DfkHandle h, const float pose0[7], const float pose1[7], const float* code0,
+                                     int code_size, const DfkCamera* cam, const DfkImage* prx_orig,
+                                     const DfkImage* prx_jac, int num_matches, const float* query_xy,
+                                     const float* train_xy, float cauchy_delta, float sigma, float* rows,
+                                     float* total_err);
+
 /* ------------------------------------------------------------------ cu_image_proc free functions */
 
 /* df::UpdateDepth (cu_image_proc.h:41-44, cu_image_proc.cpp:248-277):

@@ -174,6 +174,17 @@ void dfko_depth_run_step_d(const float* code, int code_size, int width, int heig
                            const float* prx_orig, size_t prx_pitch, const float* prx_jac, size_t jac_pitch, float avg_dpt,
                            double* JtJ, double* Jtr, double* residual, uint64_t* inliers);
 
+/* ---- ReprojectionFactor::linearize rows (core/gtsam/reprojection_factor.cpp:157-269): rows_out is
+ * (2 * num_matches) x (13 + C) row-major [J_pose0 | J_pose1 | J_code0 | b]; returns the sum of squared unweighted errors */
+float dfko_reprojection_rows_f(const float pose0[7], const float pose1[7], const float* code, int code_size,
+                               const DfkoCamera* cam, int width, int height, const float* prx_orig, size_t prx_pitch,
+                               const float* prx_jac, size_t jac_pitch, int num_matches, const float* query_xy,
+                               const float* train_xy, float cauchy_delta, float sigma, float avg_dpt, float* rows_out);
+double dfko_reprojection_rows_d(const float pose0[7], const float pose1[7], const float* code, int code_size,
+                                const DfkoCamera* cam, int width, int height, const float* prx_orig, size_t prx_pitch,
+                                const float* prx_jac, size_t jac_pitch, int num_matches, const float* query_xy,
+                                const float* train_xy, float cauchy_delta, float sigma, float avg_dpt, double* rows_out);
+
 /* ---- pyramid construction (cu_image_proc.cpp:57-92, 134-164) and SquaredError (:190-242) */
 void dfko_sobel_gradients_f(int width, int height, const float* img, size_t img_pitch,
                             float* grad /* (gx,gy) interleaved */, size_t grad_pitch);

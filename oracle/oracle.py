@@ -300,6 +300,29 @@ def depth_run_step(code, target_dpt, prx_orig, prx_jac, avg_dpt=2.0, *, precisio
     return StepResult(JtJ, Jtr, float(res.value), int(inl.value))
 
 
+def reprojection_rows(pose0, pose1, code, cam, prx_orig, prx_jac, query_xy, train_xy, cauchy_delta, sigma, avg_dpt=2.0, *,
+                      precision="f32"):
+    """ReprojectionFactor::linearize rows on the CPU (reprojection_factor.cpp:157-269).  Returns (rows [2M, 13+C], total_err)."""
+    code = np.ascontiguousarray(code, dtype=np.float32)
+    prx_orig, prx_jac = _f32(prx_orig), _f32(prx_jac)
+    H, W = prx_orig.shape
+    Cs = code.shape[0]
+    q = np.ascontiguousarray(query_xy, dtype=np.float32).reshape(-1, 2)
+    t = np.ascontiguousarray(train_xy, dtype=np.float32).reshape(-1, 2)
+    M = q.shape[0]
+    pose0 = np.ascontiguousarray(pose0, dtype=np.float32)
+    pose1 = np.ascontiguousarray(pose1, dtype=np.float32)
+    c = _cam(cam)
+    dt, ct = (np.float64, C.c_double) if precision == "f64" else (np.float32, C.c_float)
+    rows = np.zeros((2 * M, 13 + Cs), dtype=dt)
+    fn = lib().dfko_reprojection_rows_d if precision == "f64" else lib().dfko_reprojection_rows_f
+    fn.restype = ct
+    tot = fn(_ptr(pose0), _ptr(pose1), _ptr(code), C.c_int(Cs), C.byref(c), C.c_int(W), C.c_int(H), _ptr(prx_orig),
+             _pitch(prx_orig), _ptr(prx_jac), _pitch(prx_jac), C.c_int(M), _ptr(q), _ptr(t), C.c_float(cauchy_delta),
+             C.c_float(sigma), C.c_float(avg_dpt), _ptr(rows, ct))
+    return rows, float(tot)
+
+
 def sobel_gradients(img):
     img = _f32(img)
     H, W = img.shape

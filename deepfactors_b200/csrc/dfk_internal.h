@@ -75,9 +75,9 @@ struct SfmCfg {
 
 constexpr int kTilePixels = 256;    // fp32 kernel
 constexpr int kTcTilePixels = 128;  // tensor-core kernel
-// tensor-core partial: rows = TMEM lanes that carry data (32 code-h, 32 code-l, 7 pose-h, 7 pose-l),
+// tensor-core partial: rows = TMEM lanes that carry data (32 code-h, 32 code-l, 7 + 1 pose-h, 7 + 1 pose-l),
 // columns = B features (32 code, 7 pose/residual, 1 pad)
-constexpr int kTcRows = 78;
+constexpr int kTcRows = 80;
 constexpr int kTcCols = 40;
 // stored column-major with the row dimension padded to the 96 TMEM lanes of the three operand warps, so that a
 // warp's 32 lanes (rows) touch 32 consecutive floats per column: coalesced st / red

@@ -31,7 +31,7 @@ __device__ __forceinline__ int packed_index(int i, int j, int NP) { return i * N
 
 // TMEM row of the h / l part of feature f (tensor-core partial), C = 32
 __device__ __forceinline__ int tc_hrow(int f) { return f < 32 ? f : 64 + (f - 32); }
-__device__ __forceinline__ int tc_lrow(int f) { return f < 32 ? 32 + f : 71 + (f - 32); }
+__device__ __forceinline__ int tc_lrow(int f) { return f < 32 ? 32 + f : 72 + (f - 32); }
 
 template <int C, bool TC>
 __global__ void __launch_bounds__(kFinWarps * 32)

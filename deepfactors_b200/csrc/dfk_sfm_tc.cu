@@ -6,34 +6,42 @@
 //
 //   Split precision ("3xTF32" folded into ONE MMA): every feature value v is split exactly into
 //   h = the bits the tensor core keeps (fp32 -> tf32 is a truncation of the low 13 mantissa bits on
-//   this hardware, measured by tools/umma_probe.cu) and l = v - h.  With A = [h rows ; l rows] (78 of
-//   M = 128 rows) and B = h (39 of N = 48 columns), one tcgen05.mma.kind::tf32 per 8 pixels yields
-//   HH = sum h h^T and LH = sum l h^T;  G = HH + LH + LH^T  drops only the l*l terms (~2^-22).
+//   this hardware, measured by tools/umma_probe.cu) and l = v - h.  With A = [h rows ; l rows] and B = h,
+//   one tcgen05.mma.kind::tf32 per 8 pixels yields HH = sum h h^T and LH = sum l h^T;
+//   G = HH + LH + LH^T  drops only the l*l terms (~2^-22).
 //
-//   Per CTA (512 threads, 2 CTAs / SM, 256 TMEM columns each; register budgets by setmaxnreg):
-//     warps 0-7   front-end : two groups of 4 warps that alternate tiles; one thread per pixel of a 128-pixel tile:
-//                             (optional depth decode,) exact-order validity chain, bilinear gathers, Jacobian row,
-//                             Huber.  Each warp owns one 32-pixel block: valid pixels are compacted warp-locally and
-//                             the staged code-Jacobian row of a valid pixel is scaled by s = w*e and moved to its rank
-//                             IN PLACE in the ring stage; w*a[6], w*diff go to shared memory (feat).
-//     warps 8-10, operand   : two groups (A, B) of 3 warps, lane = feature row; group g builds blocks g and g+2 of
-//           12-14             every tile.  ow 0: h of the 32 code features (the raw scaled values; the tensor core
-//                             truncates), also written K-major to shared memory as B; ow 1: l of the code features;
-//                             ow 2: h and l of the 7 pose/residual features.  A goes registers -> TMEM with
-//                             tcgen05.st.32x32b.x32 (lane = row, column = pixel); the code rows are read with one
-//                             conflict-free LDS per pixel (lane = code dimension).  Group A also drains the chains.
-//     warp 11     control   : lane 0 issues the MMAs (A from TMEM, B from shared memory through a K-major no-swizzle
-//                             descriptor), the tcgen05.commit arrivals, and allocates TMEM.
-//     warp 15     producer  : lane 0 issues the cp.async.bulk copies of a tile as soon as its ring stage is free.
+//   Round-2 data path ("direct operands"): both MMA operands are read from shared memory in the PIXEL-major
+//   ("MN-major") layout a per-pixel front-end writes naturally -- canonical layout SWIZZLE_128B_BASE32B, the one the
+//   hardware defines for transposed 32-bit operands (tools/umma_probe_mn.cu: atoms of 32 features x 4 pixels, the
+//   32-byte chunk c of pixel row r stored at chunk position c ^ r).  There is no operand-building stage, no TMEM A
+//   operand, no transposition and no tile staging any more: a front-end warp goes from global memory to a finished
+//   operand block on its own and hands it to the MMA issuer with one mbarrier arrival.
+//
+//   Per CTA (512 threads, 2 CTAs / SM, 128 TMEM columns each; register budgets by setmaxnreg):
+//     warps 0-11  front-end : warp w owns the CTA's 32-pixel blocks j = w, w+12, ... (a 128-pixel tile = 4 blocks).
+//                             One thread per pixel: (optional depth decode,) exact-order validity chain, bilinear
+//                             gathers, Jacobian row, Huber -> s = w*e, w*a[6], w*diff.  Then the block's code-Jacobian
+//                             rows are read straight from global memory, COALESCED (lane = 16-byte chunk lane&7 of pixel
+//                             4i + lane/8; the rows were prefetched into L2 when the block started), scaled by the
+//                             pixel's s (one shuffle), split into h / l and stored as the code-h and code-l atoms of
+//                             an operand slot; each thread adds its own pixel's 7 pose/residual values (h and l) to the
+//                             third atom.  Invalid pixels contribute exact zeros; 8-pixel groups without a valid
+//                             pixel are skipped altogether (no loads, no MMA).
+//     warps 12-14 drain     : pull a finished accumulation chain out of TMEM (tcgen05.ld) and add it in round-to-nearest
+//                             fp32 to the CTA's partial in global memory (single writer per address, program order).
+//     warp 15     control   : lane 0 walks the blocks in order: waits for the slot, issues one MMA per non-empty
+//                             8-pixel group (A = the slot's atoms 0,1,2 (+1 junk atom: M = 128), B = atoms 0 and 2:
+//                             N = 48), commits the slot back to the front-end, cuts the chains and publishes their
+//                             records to the drain warps.  It also allocates TMEM.
+//   Operand slot (12 KB): atom a (a = 0 code-h, 1 code-l, 2 pose: h at features 0-7, l at 8-15, rest zero) at
+//   a * 4096; inside, K atom q (pixels 4q..4q+3) at q * 512, pixel row r at r * 128, 32-byte chunk c at (c ^ r) * 32.
+//   Accumulator rows (TMEM lanes): 0-31 code-h, 32-63 code-l, 64-71 pose-h, 72-79 pose-l; columns 0-31 code, 32-39 pose.
 //   The fp32 accumulator in TMEM adds with truncation (measured: ~ -2^-24 relative per k-step), so a chain is cut every
-//   kFlushTiles tiles: operand group A pulls the finished chain out of TMEM (tcgen05.ld) and adds it in round-to-nearest
-//   fp32 to the CTA's partial in global memory (single writer per address, program order => reproducible).
-//   Experiment switches (-DDFK_EXP_NOGEOM / NOCOMPACT / NOOPBUILD / NOMMA / NODRAIN: wrong results, informative
-//   times) and phase timers (-DDFK_TC_TIMERS + env DFK_TC_DEBUG=1) are kept for the roofline accounting in DESIGN.md.
+//   kFlushTiles tiles.
 //
-// Tile staging (cp.async.bulk row segments into a 4-deep ring), the static tile->CTA assignment, the
-// in-item tile permutation, the per-CTA partials and the wide deterministic finalize are those of the
-// fp32 kernel.
+// The static tile->CTA assignment, the in-item tile permutation, the per-CTA partials and the wide deterministic
+// finalize are those of the fp32 kernel.  The round-1 kernel (TMA-staged tiles, operand warps transposing into a TMEM
+// A operand) and two intermediate redesigns are kept under tools/experiments/ with their measurements.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -50,32 +58,38 @@ namespace {
 
 constexpr int C = 32;
 constexpr int TILE = kTcTilePixels;  // 128
-constexpr int FEAT_STRIDE = TILE + 4;  // floats per feature row in shared memory (see Smem::feat)
-constexpr int HALF = 64;
-constexpr int STAGES = 4;
-constexpr int FE_GROUPS = 2;         // front-end group g handles the CTA's tiles i with i % 2 == g
-constexpr int FE_THREADS = 128;      // per group: one thread per pixel of a tile
-constexpr int OP_THREADS = 256;       // warps 8-10: operand group A, 11: control, 12-14: operand group B, 15: TMA producer
-// The operand / control / producer warps take the HIGH warp ids: the sub-core arbiter favours higher warp ids, and
-// the short operand pipeline must not queue behind the eight front-end warps.
-constexpr int THREADS = OP_THREADS + FE_GROUPS * FE_THREADS;
-constexpr int NB = 48;           // MMA N (39 used)
-constexpr int MM = 128;          // MMA M (78 used)
+constexpr int NFE = 12;              // front-end warps
+constexpr int THREADS = 512;         // 12 front-end warps, 3 drain warps, control
+#ifndef DFK_TC_SLOTS
+#define DFK_TC_SLOTS 8
+#endif
+constexpr int NSLOT = DFK_TC_SLOTS;  // operand slots; block j uses slot j % NSLOT
+constexpr uint32_t ATOM_BYTES = 512;              // 32 features x 4 pixels
+constexpr uint32_t MN_STRIDE = 8 * ATOM_BYTES;    // the 8 K atoms of one MN atom are contiguous
+constexpr uint32_t SLOT_BYTES = 3 * MN_STRIDE;    // 12288
+constexpr int NB = 48;           // MMA N (40 used)
+constexpr int MM = 128;          // MMA M (80 used)
 #ifndef DFK_FLUSH_TILES
 #define DFK_FLUSH_TILES 8
 #endif
 constexpr int kFlushTiles = DFK_FLUSH_TILES;  // TMEM accumulation chain length (tiles)
-constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t A_COL = 0;    // [0,128): two 64-column halves of A
-constexpr uint32_t D_COL = 128;  // [128,176), [176,224): two accumulators
-constexpr uint32_t B_SBO = (HALF / 4) * 128;                 // 2048 B between 8-row groups
-constexpr uint32_t B_HALF_BYTES = (NB / 8) * B_SBO;           // 12288 B
-constexpr int JC_STAGE_FLOATS = (TILE + 1) * C;               // +1: an all-zero row for padded pixels
+constexpr uint32_t TMEM_COLS = 128;
+constexpr uint32_t D_COL = 0;  // [0,48), [48,96): two accumulators
 
-struct TileMeta {
-  int nv[4];         // valid pixels of the four 32-pixel blocks (each block compacted on its own)
-  int item_changed;
-  int slot;
+struct SlotMeta {
+  int mask;          // bit g: the 8-pixel group g of the block has a valid pixel
+  int nvalid;
+  int item_changed;  // the block opens a tile that is the first of its item in this CTA's sequence
+  int pslot;         // partial slot of the item
+};
+
+struct ChainRec {
+  int valid;         // valid pixels accumulated into the chain
+  int pslot;
+  int fresh;         // first chain of the item in this CTA: store, do not add
+  int item_end;
+  unsigned int inliers;
+  int last;
   int pad[2];
 };
 
@@ -91,53 +105,50 @@ struct ItemSmem {
   const float* jac;
   const float* grad1;
   const float* ray_tab;
-  float* dpt_out;  // fused depth decode: where the decoded depth goes (dpt0 then stages prx_orig)
+  float* dpt_out;  // fused depth decode: where the decoded depth goes (dpt0 then is prx_orig)
   uint32_t img0_pitch, img1_pitch, dpt0_pitch, valid0_pitch, jac_pitch, grad1_pitch, dpt_out_pitch;
   uint32_t width, height, num_pixels, tile_begin, num_tiles, perm_mul, flags, slot, mag_tiles, mag_width;
-  alignas(128) float code[C];  // fused depth decode: the latent code of the item (128-byte aligned: chunk addresses are formed by xor)
+  alignas(16) float code[C];  // fused depth decode: the latent code of the item
 };
 
 struct Smem {
-  alignas(128) float jc[STAGES][JC_STAGE_FLOATS];
-  alignas(128) unsigned char B[2][B_HALF_BYTES];
-  alignas(16) float img0[STAGES][TILE];
-  alignas(16) float dpt0[STAGES][TILE];
-  // K-major per-pixel scalars of the compacted pixels: s, wa0..5, wr.  Rows are padded by one float4 so that the pose
-  // operand warp, whose lanes read the SAME pixel chunk of 7 different rows, hits 7 different bank groups
-  alignas(16) float feat[2][8][FEAT_STRIDE];
-  alignas(16) int sid[2][TILE];        // slot (row of the jc stage) of each compacted pixel
-  alignas(8) uint64_t tma_full[STAGES];
-  uint64_t stage_empty[STAGES];  // the operand warps are done with the ring stage
-  uint64_t feat_full[2];
-  uint64_t feat_empty[2];
-  uint64_t a_full[2];
-  uint64_t a_empty[2];
+  alignas(1024) unsigned char op[NSLOT][SLOT_BYTES];
+  // >= 4 KB follow the ring: the (ignored) fourth MN atom of an M = 128 operand in the last slot reads into them
+  alignas(128) ItemSmem item[NFE];
+  alignas(8) uint64_t full[NSLOT];
+  // done[w]: the MMAs of the block that used front-end warp w's NEXT slot before it have completed.  One barrier per
+  // waiting warp, not per slot: a parity wait can only tell a phase from its neighbours, and with several independent
+  // producers per slot a per-slot barrier can be two phases away from the one a producer needs
+  uint64_t done[NFE];
   uint64_t d_full[2];
   uint64_t d_empty[2];
-  TileMeta meta[2];
-  ItemSmem item[FE_GROUPS];
+  SlotMeta meta[NSLOT];
+  ChainRec chain[2];
   uint32_t tmem_base;
 };
+static_assert(sizeof(ItemSmem) * NFE >= MN_STRIDE, "the ring's tail pad");
 
-__device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, int tid, int cta)
+// one warp copies an item description to its private shared-memory copy
+__device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, int lane, int cta)
 {
-  if (tid < 4) dst.q[tid] = src.q[tid];
-  if (tid < 3) dst.t[tid] = src.t[tid];
-  if (tid < 9) dst.R[tid] = src.R[tid];
-  if (tid == 32) {
+  if (lane < 4) dst.q[lane] = src.q[lane];
+  if (lane >= 4 && lane < 7) dst.t[lane - 4] = src.t[lane - 4];
+  if (lane >= 8 && lane < 17) dst.R[lane - 8] = src.R[lane - 8];
+  if (lane == 17) {
     dst.fx = src.fx; dst.fy = src.fy; dst.u0 = src.u0; dst.v0 = src.v0;
     dst.border = src.border; dst.ulim = src.ulim; dst.vlim = src.vlim;
     dst.min_dpt = src.min_dpt; dst.avg_dpt = src.avg_dpt; dst.huber_delta = src.huber_delta;
   }
-  if (tid == 64) {
+  if (lane == 18) {
     dst.img0 = src.img0; dst.img1 = src.img1; dst.dpt0 = src.dpt0; dst.valid0 = src.valid0;
     dst.jac = src.jac; dst.grad1 = src.grad1; dst.ray_tab = src.ray_tab;
-    dst.img0_pitch = src.img0_pitch; dst.img1_pitch = src.img1_pitch; dst.dpt0_pitch = src.dpt0_pitch;
-    dst.valid0_pitch = src.valid0_pitch; dst.jac_pitch = src.jac_pitch; dst.grad1_pitch = src.grad1_pitch;
     dst.dpt_out = src.dpt_out; dst.dpt_out_pitch = src.dpt_out_pitch;
   }
-  if (tid >= 64 && tid < 64 + C && (src.flags & ITEM_FLAG_FUSED_DEPTH)) dst.code[tid - 64] = __ldg(src.code + (tid - 64));
-  if (tid == 96) {
+  if (lane == 19) {
+    dst.img0_pitch = src.img0_pitch; dst.img1_pitch = src.img1_pitch; dst.dpt0_pitch = src.dpt0_pitch;
+    dst.valid0_pitch = src.valid0_pitch; dst.jac_pitch = src.jac_pitch; dst.grad1_pitch = src.grad1_pitch;
+  }
+  if (lane == 20) {
     dst.width = src.width; dst.height = src.height; dst.num_pixels = src.num_pixels;
     dst.tile_begin = src.tile_begin; dst.num_tiles = src.num_tiles; dst.perm_mul = src.perm_mul;
     dst.flags = src.flags;
@@ -145,51 +156,7 @@ __device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, 
     dst.mag_width = src.mag_width;
     dst.slot = src.partial_begin + (uint32_t)cta - src.first_cta;
   }
-}
-
-// with_scalars: also stage img0 / dpt0 (only the fused depth decode reads them from the stage; otherwise the front-end
-// threads fetch their own pixel with two coalesced loads long before the tile lands)
-__device__ __forceinline__ void issue_tile_loads(Smem& sm, const SfmItemDev* __restrict__ items, int it, int g, int st)
-{
-  const SfmItemDev& I = items[it];
-  const bool with_scalars = (I.flags & ITEM_FLAG_FUSED_DEPTH) != 0;
-  const uint32_t k = (uint32_t)g - I.tile_begin;
-  const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
-  const uint32_t p0 = tau * TILE;
-  const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
-  const uint32_t W = I.width;
-  uint32_t y = p0 / W;
-  uint32_t x = p0 - y * W;
-  mbar_arrive_expect_tx(&sm.tma_full[st], n * (C + (with_scalars ? 2 : 0)) * 4u);
-  uint32_t slot = 0;
-  while (slot < n) {
-    const uint32_t seg = min(W - x, n - slot);
-    bulk_g2s(&sm.jc[st][slot * C], I.jac + (size_t)y * I.jac_pitch + (size_t)x * C, seg * C * 4u, &sm.tma_full[st]);
-    if (with_scalars) {
-      bulk_g2s(&sm.img0[st][slot], I.img0 + (size_t)y * I.img0_pitch + x, seg * 4u, &sm.tma_full[st]);
-      bulk_g2s(&sm.dpt0[st][slot], I.dpt0 + (size_t)y * I.dpt0_pitch + x, seg * 4u, &sm.tma_full[st]);
-    }
-    slot += seg;
-    x = 0;
-    ++y;
-  }
-}
-
-__device__ __forceinline__ void coop_tile_loads(Smem& sm, const ItemSmem& I, uint32_t p0, uint32_t n, int st, int ft)
-{
-  const uint32_t W = I.width;
-  for (uint32_t s = ft; s < n; s += FE_THREADS) {
-    const uint32_t p = p0 + s;
-    const uint32_t y = p / W, x = p - y * W;
-    sm.img0[st][s] = __ldg(I.img0 + (size_t)y * I.img0_pitch + x);
-    sm.dpt0[st][s] = __ldg(I.dpt0 + (size_t)y * I.dpt0_pitch + x);
-  }
-  for (uint32_t e = ft; e < n * C; e += FE_THREADS) {
-    const uint32_t s = e / C, kk = e - s * C;
-    const uint32_t p = p0 + s;
-    const uint32_t y = p / W, x = p - y * W;
-    sm.jc[st][e] = __ldg(I.jac + (size_t)y * I.jac_pitch + (size_t)x * C + kk);
-  }
+  if (src.flags & ITEM_FLAG_FUSED_DEPTH) dst.code[lane] = __ldg(src.code + lane);
 }
 
 // a / b and a % b through the precomputed mag = floor(2^32 / b): multiply-high, one correction step
@@ -206,41 +173,41 @@ __device__ __forceinline__ uint32_t div_magic(uint32_t a, uint32_t b, uint32_t m
 }
 __device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
-// ---- optional phase timers (clock64 sums per role), enabled with the env var DFK_TC_DEBUG=1 ----------
-// Compiled in only with -DDFK_TC_TIMERS (they cost ~40 instructions per tile and role).
-__device__ unsigned long long g_dbg[16];
-#ifdef DFK_TC_TIMERS
-struct Tmr {
-  long long t;
-  bool on;
-  __device__ __forceinline__ void start() { if (on) t = clock64(); }
-  __device__ __forceinline__ void lap(unsigned long long& acc) { if (on) { const long long n = clock64(); acc += (unsigned long long)(n - t); t = n; } }
-};
+// -DDFK_TC_WATCHDOG: a wait that gives up after ~1 s, says who was waiting for what, and traps (bring-up aid: a
+// protocol error becomes a CUDA error with a message instead of a hung device)
+#ifdef DFK_TC_WATCHDOG
+__device__ __noinline__ void wd_wait(uint64_t* bar, uint32_t parity, int what, int idx)
+{
+  for (long long spin = 0; spin < 2000000; ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+  if ((threadIdx.x & 31) == 0)
+    printf("[dfk tc watchdog] cta %d warp %d stuck: wait %d index %d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), what,
+           idx, parity);
+  __trap();
+}
+#define TC_WAIT(bar, parity, what, idx) wd_wait(bar, parity, what, idx)
 #else
-struct Tmr {
-  long long t;
-  bool on;
-  __device__ __forceinline__ void start() {}
-  __device__ __forceinline__ void lap(unsigned long long&) {}
-};
+#define TC_WAIT(bar, parity, what, idx) mbar_wait(bar, parity)
 #endif
 
-// chain bookkeeping shared (by construction) between the control thread and the operand warps
-struct ChainState {
-  int e = -1;              // current chain index
-  int tiles_in_chain = 0;
-  __device__ __forceinline__ bool starts_chain(int i, int item_changed) const
-  {
-    return i == 0 || item_changed != 0 || tiles_in_chain == kFlushTiles;
-  }
-};
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d)
+{
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// 16 bytes of a code-Jacobian row; rows of items without the BULK flag are only 4-byte aligned
+__device__ __forceinline__ float4 load_chunk(const float* __restrict__ p, bool aligned16)
+{
+  if (aligned16) return __ldg(reinterpret_cast<const float4*>(p));
+  return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
 
 __global__ void __launch_bounds__(THREADS, 2)
-sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_tiles, float* __restrict__ partials,
-                   int dbg)
+sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_tiles, float* __restrict__ partials)
 {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  extern __shared__ unsigned char smem_raw[];
+  // the swizzle pattern of the operand atoms is a function of the shared-memory address bits: 1024-byte aligned ring
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
@@ -249,28 +216,25 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
   const int g_lo = (int)(((long long)cta * num_tiles) / G);
   const int g_hi = (int)(((long long)(cta + 1) * num_tiles) / G);
   const int ntiles = g_hi - g_lo;
+  const int nblocks = 4 * ntiles;
+  (void)num_items;
 
   // ---- one-time setup ---------------------------------------------------------------------------
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&sm.tma_full[s], 1);
-      mbar_init(&sm.stage_empty[s], 6);
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&sm.full[s], 1);
     }
+    for (int w = 0; w < NFE; ++w) mbar_init(&sm.done[w], 1);
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&sm.feat_full[b], FE_THREADS / 32);  // one arrival per front-end warp: every arrival wakes the waiters
-      mbar_init(&sm.feat_empty[b], 7);  // 2 x 3 operand warps + the control thread (it reads meta[b])
-      mbar_init(&sm.a_full[b], 6);
-      mbar_init(&sm.a_empty[b], 1);
-      mbar_init(&sm.d_full[b], 1);
+      mbar_init(&sm.d_full[b], 2);   // the tcgen05.commit of the chain's MMAs + the control thread's release of the record
       mbar_init(&sm.d_empty[b], 3);
     }
     mbar_fence_init();
   }
-  // zero row of every jc stage and the whole B buffer (rows 39..47 are never written again)
-  for (int s = 0; s < STAGES; ++s)
-    if (tid < C) sm.jc[s][TILE * C + tid] = 0.0f;
-  for (int e = tid; e < (int)(2 * B_HALF_BYTES / 4); e += THREADS) reinterpret_cast<float*>(sm.B)[e] = 0.0f;
-  if (warp == 11) {
+  // the never-written parts of the ring (pose atom chunks 2, 3) must hold zeros
+  for (int e = tid; e < (int)(NSLOT * SLOT_BYTES / 16); e += THREADS)
+    reinterpret_cast<float4*>(&sm.op[0][0])[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp == 15) {
     tmem_alloc(&sm.tmem_base, TMEM_COLS);
     tmem_relinquish();
   }
@@ -280,495 +244,284 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
   tc_fence_after();
   const uint32_t tbase = sm.tmem_base;
 
-  // register budget per role (warpgroup granularity): operand / control warps are lean, the front-end is not
-  if (warp < 8) {
+  // register budget per role (warpgroup granularity): 12 x 32 x 72 + 4 x 32 x 40 = 32768 = half the register file
+  if (warp < NFE) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   }
 
   if (ntiles > 0) {
-    if (warp < 8) {
-      // ======================================================================= front-end groups
-      const int grp = warp >> 2;                // 0 / 1
-      const int ft = tid & (FE_THREADS - 1);    // 0..127 = pixel slot
-      const int fwarp = warp & 3;
-      const uint32_t bar_id = 1 + grp;
-      ItemSmem& I = sm.item[grp];
+    if (warp < NFE) {
+      // ======================================================================= front-end warps
+      ItemSmem& I = sm.item[warp];
       int it = 0;
-      uint32_t tma_phase_bits = 0;
       int cur_item = -1;
       uint32_t item_lo = 0, item_hi = 0;  // global tile range of the item in shared memory
-#ifdef DFK_TC_TIMERS
-      Tmr tm{0, dbg != 0 && ft == 0};
-#else
-      Tmr tm{0, false};
-#endif
-      unsigned long long t_tma = 0, t_geo = 0, t_fe_wait = 0, t_fe_write = 0, t_issue_fe = 0;
-      for (int i = grp; i < ntiles; i += FE_GROUPS) {
+      uint32_t done_phase = 0;
+      for (int j = warp; j < nblocks; j += NFE) {
+        const int i = j >> 2, b = j & 3;
         const int g = g_lo + i;
-        const int st = i % STAGES;
-        const int fb = grp;  // == i & 1
-        if ((uint32_t)g >= item_hi || cur_item < 0) {
+        if (cur_item < 0 || (uint32_t)g >= item_hi) {
           while ((uint32_t)g >= items[it].tile_begin + items[it].num_tiles) ++it;
-          named_bar_sync(bar_id, FE_THREADS);
-          load_item(I, items[it], ft, cta);
+          __syncwarp();
+          load_item(I, items[it], lane, cta);
+          __syncwarp();
           cur_item = it;
-          named_bar_sync(bar_id, FE_THREADS);
           item_lo = I.tile_begin;
           item_hi = I.tile_begin + I.num_tiles;
         }
-        // the tile sequence enters a new item here (relative to tile i-1, which the other group handles)
-        const bool seq_changed = (i == 0) || ((uint32_t)(g - 1) < item_lo);
+        // the tile sequence enters a new item with this block
+        const bool seq_changed = (b == 0) && ((i == 0) || ((uint32_t)(g - 1) < item_lo));
         const uint32_t k = (uint32_t)g - item_lo;
         uint32_t tau;
         div_magic(k * I.perm_mul, I.num_tiles, I.mag_tiles, tau);  // host guarantees k * perm_mul < 2^32
         const uint32_t p0 = tau * TILE;
         const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
-        const bool bulk = (I.flags & ITEM_FLAG_BULK) != 0;
-        const uint32_t s = ft;
-        // tile origin (uniform) by one division, then this thread's pixel by wrap-around
+        const uint32_t s = 32u * (uint32_t)b + (uint32_t)lane;  // pixel slot in the tile
+        const bool inb = s < n;
+        const bool blk_live = 32u * (uint32_t)b < n;  // else: a block past the end of the item's last tile
+        const uint32_t W = I.width;
+        const bool a16 = (I.flags & ITEM_FLAG_BULK) != 0;
+        const bool fused = (I.flags & ITEM_FLAG_FUSED_DEPTH) != 0;
+        // block origin (uniform) by one division, then this thread's pixel by wrap-around; lanes past the end of the
+        // tile shadow the block's first pixel (their loads stay in bounds, their contribution is zero)
         uint32_t x0;
-        const uint32_t y0 = div_magic(p0, I.width, I.mag_width, x0);
-        uint32_t pxx = x0 + (s < n ? s : 0u), py = y0;
-        while (pxx >= I.width) {
-          pxx -= I.width;
+        const uint32_t y0 = div_magic(blk_live ? p0 + 32u * (uint32_t)b : p0, W, I.mag_width, x0);
+        uint32_t pxx = x0 + (inb ? (uint32_t)lane : 0u), py = y0;
+        while (pxx >= W) {
+          pxx -= W;
           ++py;
         }
-        const float xn = __ldg(I.ray_tab + pxx);              // in flight while the tile lands
-        const float yn = __ldg(I.ray_tab + I.width + py);
-        // The tile's code-Jacobian rows are needed only after the geometry (compaction), so a bulk-staged tile is waited
-        // for THERE: this thread's own dpt0 / img0 come straight from global memory (coalesced, issued now).  The fused
-        // depth decode reads the rows first thing and keeps the early wait.
-        const bool early = !bulk || (I.flags & ITEM_FLAG_FUSED_DEPTH) != 0;
-        float d_g = 0.0f, i0_g = 0.0f;
-        if (!early && s < n) {
-          d_g = __ldg(I.dpt0 + (size_t)py * I.dpt0_pitch + pxx);
-          i0_g = __ldg(I.img0 + (size_t)py * I.img0_pitch + pxx);
-        }
-        tm.start();
-        if (bulk) {
-          if (early) {
-            mbar_wait_parked(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
-            tma_phase_bits ^= (1u << st);
-          }
-        } else {
-          // stage st was last read by the operand warps of tile i-4 (stage_empty / feat_empty completed)
-          coop_tile_loads(sm, I, p0, n, st, ft);
-          named_bar_sync(bar_id, FE_THREADS);
-        }
-        tm.lap(t_tma);
-
+        const uint32_t joff = py * I.jac_pitch + pxx * C;  // this pixel's code-Jacobian row (floats)
         float feat[8];
         bool ok = false;
-#ifdef DFK_EXP_NOGEOM
-        if (s < n) {
-          ok = (s & 3u) != 0u;
-          const float d = sm.dpt0[st][s];
+        if (blk_live) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(I.jac + joff));
+          const float xn = __ldg(I.ray_tab + pxx);
+          const float yn = __ldg(I.ray_tab + W + py);
+          float d = __ldg(I.dpt0 + (size_t)py * I.dpt0_pitch + pxx);
+          const float i0 = __ldg(I.img0 + (size_t)py * I.img0_pitch + pxx);
+          if (fused) {
+            // dpt0 is prx_orig: decode the depth from the pixel's code-Jacobian row -- same arithmetic as
+            // update_depth_kernel (chunk fma chains, then the xor-butterfly over the 8 chunk sums, here ACROSS the 8
+            // lanes that hold the chunks of one pixel), publish it, and carry on with it
+            const float4 cc = *reinterpret_cast<const float4*>(&I.code[4 * (lane & 7)]);
+            float mine = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) feat[j] = 0.001f * (float)(j + 1) * d + xn * yn;
-          if (ok) I.valid0[(size_t)py * I.valid0_pitch + pxx] = 1.0f;
-        }
-        if (false) {
-          const uint32_t y = py, x = pxx;
-#else
-        if (s < n) {
-          const uint32_t y = py, x = pxx;
-#endif
-          float d = early ? sm.dpt0[st][s] : d_g;
-          if (I.flags & ITEM_FLAG_FUSED_DEPTH) {
-            // the stage holds prx_orig: decode the depth from this pixel's code-Jacobian row (same arithmetic as
-            // update_depth_kernel: chunk fma chains + xor-butterfly; register j holds chunk j ^ (lane & 7), which the
-            // butterfly does not care about), publish it, and carry on with it
-            const uint32_t src = smem_u32(&sm.jc[st][s * C]) + ((uint32_t)(lane & 7) << 4);
-            const uint32_t cod = smem_u32(I.code) + ((uint32_t)(lane & 7) << 4);
-            float part[C / 4];
-#pragma unroll
-            for (int k4 = 0; k4 < C / 4; ++k4) {
-              float4 v, c;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src ^ ((uint32_t)k4 << 4)));
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "r"(cod ^ ((uint32_t)k4 << 4)));
-              part[k4] = chunk_dot(v, c);
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const uint32_t offk = __shfl_sync(0xffffffffu, joff, 4 * i8 + (lane >> 3));
+              float p = chunk_dot(load_chunk(I.jac + offk + 4 * (lane & 7), a16), cc);
+              p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 4));
+              p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 2));
+              p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 1));
+              const float got = __shfl_sync(0xffffffffu, p, 8 * (lane & 3));  // pixel 4 i8 + (lane & 3)
+              if ((lane >> 2) == i8) mine = got;
             }
-            d = prx_to_depth(__fadd_rn(d, butterfly_sum<C / 4>(part)), I.avg_dpt);
-            I.dpt_out[(size_t)y * I.dpt_out_pitch + x] = d;
+            d = prx_to_depth(__fadd_rn(d, mine), I.avg_dpt);
+            if (inb) I.dpt_out[(size_t)py * I.dpt_out_pitch + pxx] = d;
           }
-          const Warped w = warp_ray(xn, yn, d, I.q, I.t, I.fx, I.fy, I.u0, I.v0, I.border, I.ulim, I.vlim, I.min_dpt);
-          if (w.valid) {
-            ok = true;
-            I.valid0[(size_t)y * I.valid0_pitch + x] = 1.0f;  // dense_sfm.h:161
-            int ix, iy;
-            float fu, fv, gx, gy;
-            bilin_setup(w.u, w.v, ix, iy, fu, fv);
-            sample_grad(I.grad1, I.grad1_pitch, true, ix, iy, fu, fv, gx, gy);  // the API guarantees 8-byte rows here
-            const float i1 = sample_scalar(I.img1, I.img1_pitch, ix, iy, fu, fv);
-            float a[6], c00, c02, c11, c12;
-            pose_jacobian_row(w, I.fx, I.fy, gx, gy, a, c00, c02, c11, c12);
-            const float e = prx_jacobian(w, I.R, d, I.avg_dpt, gx, gy, c00, c02, c11, c12);
-            const float diff = (early ? sm.img0[st][s] : i0_g) - i1;
-            const float hw = huber_weight(diff, I.huber_delta);
-            feat[0] = hw * e;
+          if (inb) {
+            const Warped w = warp_ray(xn, yn, d, I.q, I.t, I.fx, I.fy, I.u0, I.v0, I.border, I.ulim, I.vlim, I.min_dpt);
+            if (w.valid) {
+              ok = true;
+              I.valid0[(size_t)py * I.valid0_pitch + pxx] = 1.0f;  // dense_sfm.h:161
+              int ix, iy;
+              float fu, fv, gx, gy;
+              bilin_setup(w.u, w.v, ix, iy, fu, fv);
+              sample_grad(I.grad1, I.grad1_pitch, true, ix, iy, fu, fv, gx, gy);  // the API guarantees 8-byte rows here
+              const float i1 = sample_scalar(I.img1, I.img1_pitch, ix, iy, fu, fv);
+              float a[6], c00, c02, c11, c12;
+              pose_jacobian_row(w, I.fx, I.fy, gx, gy, a, c00, c02, c11, c12);
+              const float e = prx_jacobian(w, I.R, d, I.avg_dpt, gx, gy, c00, c02, c11, c12);
+              const float diff = i0 - i1;
+              const float hw = huber_weight(diff, I.huber_delta);
+              feat[0] = hw * e;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) feat[1 + j] = hw * a[j];
-            feat[7] = hw * diff;
+              for (int f = 0; f < 6; ++f) feat[1 + f] = hw * a[f];
+              feat[7] = hw * diff;
+            }
           }
         }
-        // ---- warp-local compaction: this warp owns the 32-pixel block `fwarp` of the tile -----------
+        if (!ok) {
+#pragma unroll
+          for (int f = 0; f < 8; ++f) feat[f] = 0.0f;
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        const int rank = __popc(bal & ((1u << lane) - 1u));
         const int nvb = __popc(bal);
-        const int padded = (nvb + 7) & ~7;
-        // In-place compaction of the staged code-Jacobian rows of the block, scaled by s = w*e on the way:
-        // row 32*fwarp + r becomes the r-th VALID pixel's  s * jc[0..31]  (what the operand warps feed to the
-        // tensor core).  Rotated float4 order keeps reads (row = slot) and writes (row = rank) free of bank
-        // conflicts; all rows are read into registers before any is overwritten (same warp => __syncwarp).
-        if (bulk && !early) {  // now the rows are needed
-          mbar_wait_parked(&sm.tma_full[st], (tma_phase_bits >> st) & 1u);
-          tma_phase_bits ^= (1u << st);
+        const int mask = ((bal & 0xffu) ? 1 : 0) | ((bal & 0xff00u) ? 2 : 0) | ((bal & 0xff0000u) ? 4 : 0) |
+                         ((bal & 0xff000000u) ? 8 : 0);
+        // ---- the operand slot: free once the MMAs of block j - NSLOT have completed (the control thread commits them
+        // to this warp's barrier; one commit per block of this warp, in order) ------------------------------------------
+        const int slot = j % NSLOT;
+        if (j >= NSLOT) {
+          TC_WAIT(&sm.done[warp], done_phase, 0, j);
+          done_phase ^= 1u;
         }
-        float4 rowv[C / 4];
-#ifdef DFK_EXP_NOCOMPACT
-        if (false) {
-#else
-        if (ok) {
-#endif
-          // rows are 128-byte aligned: chunk (k4 ^ (lane & 7)) of row s  ==  (row address + (lane & 7) * 16) ^ (k4 * 16)
-          const uint32_t src = smem_u32(&sm.jc[st][s * C]) + ((uint32_t)(lane & 7) << 4);
+        if (nvb > 0) {
+          const uint32_t sbase = smem_u32(&sm.op[slot][0]);
+          // code atoms: iteration i8 covers the K atom of pixels 4 i8 .. 4 i8 + 3; this lane holds the 16-byte chunk
+          // lane & 7 of pixel 4 i8 + lane / 8 -> 512 contiguous bytes per warp load
+          const int r = lane >> 3;
+          const uint32_t dst0 = sbase + (uint32_t)r * 128u + (uint32_t)(((((lane & 7) >> 1) ^ r) << 5) | ((lane & 1) << 4));
+          float4 v[8];
 #pragma unroll
-          for (int k4 = 0; k4 < C / 4; ++k4) {
-            const uint32_t addr = src ^ ((uint32_t)k4 << 4);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(rowv[k4].x), "=f"(rowv[k4].y), "=f"(rowv[k4].z), "=f"(rowv[k4].w)
-                         : "r"(addr));
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int kp = 4 * i8 + r;
+            const uint32_t offk = __shfl_sync(0xffffffffu, joff, kp);
+            v[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((bal >> kp) & 1u) v[i8] = load_chunk(I.jac + offk + 4 * (lane & 7), a16);
           }
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const float sk = __shfl_sync(0xffffffffu, feat[0], 4 * i8 + r);
+            if ((mask >> (i8 >> 1)) & 1) {
+              const float h0 = sk * v[i8].x, h1 = sk * v[i8].y, h2 = sk * v[i8].z, h3 = sk * v[i8].w;
+              const uint32_t dst = dst0 + (uint32_t)i8 * ATOM_BYTES;
+              sts128(dst, h0, h1, h2, h3);  // the tensor core truncates: h rows carry the raw values
+              sts128(dst + MN_STRIDE, h0 - tf32_trunc(h0), h1 - tf32_trunc(h1), h2 - tf32_trunc(h2), h3 - tf32_trunc(h3));
+            }
+          }
+          // pose atom: this thread's pixel = K position `lane`: h of the 7 pose / residual values in chunk 0, l in chunk 1
+          {
+            const int rp = lane & 3;
+            const uint32_t row = sbase + 2u * MN_STRIDE + (uint32_t)(lane >> 2) * ATOM_BYTES + (uint32_t)rp * 128u;
+            const uint32_t ch = row + ((uint32_t)rp << 5);         // chunk 0 ^ rp
+            const uint32_t cl = row + ((uint32_t)(rp ^ 1) << 5);   // chunk 1 ^ rp
+            sts128(ch, feat[1], feat[2], feat[3], feat[4]);
+            sts128(ch + 16u, feat[5], feat[6], feat[7], 0.0f);
+            sts128(cl, feat[1] - tf32_trunc(feat[1]), feat[2] - tf32_trunc(feat[2]), feat[3] - tf32_trunc(feat[3]),
+                   feat[4] - tf32_trunc(feat[4]));
+            sts128(cl + 16u, feat[5] - tf32_trunc(feat[5]), feat[6] - tf32_trunc(feat[6]), feat[7] - tf32_trunc(feat[7]), 0.0f);
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA's operand fetch
+        }
+        if (lane == 0) {
+          sm.meta[slot].mask = mask;
+          sm.meta[slot].nvalid = nvb;
+          sm.meta[slot].item_changed = seq_changed ? 1 : 0;
+          sm.meta[slot].pslot = (int)I.slot;
         }
         __syncwarp();
-        tm.lap(t_geo);
-        // feat[fb] of tile i-2 must have been consumed by the operand warps
-        mbar_wait_parked(&sm.feat_empty[fb], ((i >> 1) & 1u) ^ 1u);
-        tm.lap(t_fe_wait);
-        const int blk0 = 32 * fwarp;
-        if (ok) {
-          const int c = blk0 + rank;
-          const float sc = feat[0];
-          const uint32_t dst = smem_u32(&sm.jc[st][c * C]) + ((uint32_t)(lane & 7) << 4);
-#ifndef DFK_EXP_NOCOMPACT
-#pragma unroll
-          for (int k4 = 0; k4 < C / 4; ++k4) {
-            const float4 v = rowv[k4];
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst ^ ((uint32_t)k4 << 4)), "f"(sc * v.x),
-                         "f"(sc * v.y), "f"(sc * v.z), "f"(sc * v.w)
-                         : "memory");
-          }
-#else
-          (void)sc; (void)dst;
-#endif
-#pragma unroll
-          for (int f = 1; f < 8; ++f) sm.feat[fb][f][c] = feat[f];
-        }
-        // pad the block's list to a multiple of 8 with "pixels" that contribute exactly zero
-        if (lane < padded - nvb) {
-          const int c = blk0 + nvb + lane;
-          float4* dst = reinterpret_cast<float4*>(&sm.jc[st][c * C]);
-#pragma unroll
-          for (int k4 = 0; k4 < C / 4; ++k4) dst[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int f = 1; f < 8; ++f) sm.feat[fb][f][c] = 0.0f;
-        }
-        if (lane == 0) sm.meta[fb].nv[fwarp] = nvb;
-        if (ft == 0) {
-          sm.meta[fb].item_changed = seq_changed ? 1 : 0;
-          sm.meta[fb].slot = (int)I.slot;
-        }
-        __syncwarp();  // the warp's rows / feat entries / meta are ordered before lane 0's release
-        if (lane == 0) mbar_arrive(&sm.feat_full[fb]);
-        tm.lap(t_fe_write);
-      }
-      if (tm.on) {
-        atomicAdd(&g_dbg[0], t_tma); atomicAdd(&g_dbg[1], t_geo); atomicAdd(&g_dbg[2], t_fe_wait);
-        atomicAdd(&g_dbg[3], t_fe_write); atomicAdd(&g_dbg[13], t_issue_fe);
-      }
-    } else if (warp == 11) {
-      // ======================================================================= control warp
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc_tf32(MM, NB);
-        ChainState ch;
-        bool first = true;
-#ifdef DFK_TC_TIMERS
-        Tmr tm{0, dbg != 0};
-#else
-        Tmr tm{0, false};
-#endif
-        unsigned long long t_afull = 0, t_issue = 0;
-        for (int i = 0; i < ntiles; ++i) {
-          const int fb = i & 1;
-          TileMeta meta{};
-          for (int h = 0; h < 2; ++h) {
-            tm.start();
-            mbar_wait_parked(&sm.a_full[h], i & 1u);
-            tc_fence_after();
-            tm.lap(t_afull);
-            if (h == 0) {
-              meta = sm.meta[fb];
-              mbar_arrive(&sm.feat_empty[fb]);  // meta[fb] may now be overwritten (once the operand warps agree)
-              if (ch.starts_chain(i, meta.item_changed)) {
-                if (i > 0) umma_commit(&sm.d_full[ch.e & 1]);
-                ch.e += 1;
-                ch.tiles_in_chain = 0;
-                first = true;
-                const int use = ch.e >> 1;  // n-th use of this accumulator buffer
-                if (use >= 1) {
-                  mbar_wait_parked(&sm.d_empty[ch.e & 1], (use - 1) & 1u);
-                  tc_fence_after();
-                }
-              }
-              ch.tiles_in_chain += 1;
-            }
-            const uint32_t d_addr = tbase + D_COL + NB * (ch.e & 1);
-            const uint64_t bdesc0 = make_smem_desc_kmajor_noswizzle(smem_u32(sm.B[h]), 128, B_SBO);
-#pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {  // the two 32-pixel blocks of the half
-              const int nk = (meta.nv[2 * h + bb] + 7) >> 3;
-              for (int ks = 0; ks < nk; ++ks) {
-                const int kc = 4 * bb + ks;  // 8-pixel k-step inside the half
-#ifndef DFK_EXP_NOMMA
-                umma_tf32_ts(d_addr, tbase + A_COL + HALF * h + 8 * kc, bdesc0 + (uint64_t)((kc * 256) >> 4), idesc, !first);
-#endif
-                first = false;
-              }
-            }
-            umma_commit(&sm.a_empty[h]);
-            tm.lap(t_issue);
-          }
-        }
-        umma_commit(&sm.d_full[ch.e & 1]);
-        if (tm.on) { atomicAdd(&g_dbg[4], t_afull); atomicAdd(&g_dbg[5], t_issue); }
+        if (lane == 0) mbar_arrive(&sm.full[slot]);
       }
     } else if (warp == 15) {
-      // ======================================================================= TMA producer (one thread)
-      // Tile j is issued as soon as its ring stage is free (tile j-4 consumed), i.e. up to three tiles ahead of
-      // the operand warps; issuing bulk copies costs hundreds of cycles apiece, so it lives on its own warp.
+      // ======================================================================= control warp
       if (lane == 0) {
-        int it_pf = 0;
-        for (int j = 0; j < ntiles; ++j) {
-          const int g = g_lo + j;
-          if (j >= STAGES) mbar_wait_parked(&sm.stage_empty[j % STAGES], ((j / STAGES) - 1) & 1u);
-          while ((uint32_t)g >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
-          if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads(sm, items, it_pf, g, j % STAGES);
+        const uint32_t idesc = make_idesc_tf32(MM, NB) | kIdescAMnMajor | kIdescBMnMajor;
+        int e = -1, tiles_in_chain = 0;
+        bool first = true;
+        int chain_valid = 0, cur_pslot = -1;
+        bool slot_fresh = true;
+        unsigned int inliers = 0;
+        // close chain e: publish its record, then let the drain warps go once its MMAs have completed
+        auto close_chain = [&](bool item_end, bool last) {
+          ChainRec& r = sm.chain[e & 1];
+          r.valid = chain_valid;
+          r.pslot = cur_pslot;
+          r.fresh = slot_fresh ? 1 : 0;
+          r.item_end = item_end ? 1 : 0;
+          r.inliers = inliers;
+          r.last = last ? 1 : 0;
+          slot_fresh = false;
+          umma_commit(&sm.d_full[e & 1]);
+          mbar_arrive(&sm.d_full[e & 1]);
+        };
+        for (int j = 0; j < nblocks; ++j) {
+          const int slot = j % NSLOT;
+          TC_WAIT(&sm.full[slot], (uint32_t)(j / NSLOT) & 1u, 1, j);
+          tc_fence_after();
+          const SlotMeta meta = sm.meta[slot];
+          if ((j & 3) == 0) {
+            if (j == 0 || meta.item_changed != 0 || tiles_in_chain == kFlushTiles) {
+              if (j > 0) close_chain(meta.item_changed != 0, false);
+              e += 1;
+              tiles_in_chain = 0;
+              chain_valid = 0;
+              first = true;
+              const int use = e >> 1;  // n-th use of this accumulator buffer (and of its record)
+              if (use >= 1) {
+                TC_WAIT(&sm.d_empty[e & 1], (uint32_t)(use - 1) & 1u, 2, e);
+                tc_fence_after();
+              }
+              if (j == 0 || meta.item_changed != 0) {
+                cur_pslot = meta.pslot;
+                slot_fresh = true;
+                inliers = 0;
+              }
+            }
+            tiles_in_chain += 1;
+          }
+          chain_valid += meta.nvalid;
+          inliers += (unsigned)meta.nvalid;
+          const uint32_t d_addr = tbase + D_COL + NB * (uint32_t)(e & 1);
+          const uint32_t sbase = smem_u32(&sm.op[slot][0]);
+          const uint64_t adesc = make_smem_desc_mn_sw128_32b(sbase, MN_STRIDE, ATOM_BYTES);
+          const uint64_t bdesc = make_smem_desc_mn_sw128_32b(sbase, 2 * MN_STRIDE, ATOM_BYTES);
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            if ((meta.mask >> gq) & 1) {
+              const uint64_t adv = (uint64_t)((2u * ATOM_BYTES * (uint32_t)gq) >> 4);  // two K atoms per k-step
+              umma_tf32_ss(d_addr, adesc + adv, bdesc + adv, idesc, !first);
+              first = false;
+            }
+          }
+          umma_commit(&sm.done[(j + NSLOT) % NFE]);  // the slot's next user: block j + NSLOT
         }
+        close_chain(true, true);
       }
-    } else if ((warp & 3) != 3) {
-      // ======================================================================= operand warps
-      // group A (warps 0-2) builds half 0 of every tile and drains the accumulators; group B (warps 4-6)
-      // builds half 1.  ow: 0 = code-h (+B), 1 = code-l, 2 = pose/residual h+l.
-      const int ogrp = (warp - 8) >> 2;
-      const int ow = warp & 3;
+    } else {
+      // ======================================================================= drain warps (TMEM lanes 0..95)
+      const int ow = warp & 3;  // 0, 1, 2 = the lane quarter this warp may access
       const uint32_t lane_taddr = tbase + ((uint32_t)(ow * 32) << 16);
       const int row = ow * 32 + lane;  // TMEM lane == row of the partial
-      ChainState ch;
-      int chain_valid = 0;        // valid pixels accumulated into the current chain
-      int cur_slot = -1;
-      bool slot_fresh = true;     // the current item's partial has not been written yet by this CTA
-      unsigned int inliers = 0;   // of the current item (warp 0 reports)
-      // deferred drain of a finished chain
-      bool pend = false;
-      int pend_e = 0, pend_valid = 0, pend_slot = 0;
-      bool pend_fresh = false, pend_item_end = false;
-      unsigned int pend_inliers = 0;
-
-      // Move a finished chain TMEM -> the CTA's partial in global memory (single writer, fixed order).
-      // fresh: first chain of the item in this CTA (store), else read-modify-write in round-to-nearest fp32.
-      auto drain = [&](int e, int valid, int slot, bool fresh, bool item_end, unsigned int inl) {
+      for (int e = 0;; ++e) {
         const int b = e & 1, use = e >> 1;
-        float* P = partials + (size_t)slot * kTcPartialFloats;
-        mbar_wait(&sm.d_full[b], use & 1u);
+        TC_WAIT(&sm.d_full[b], (uint32_t)use & 1u, 3, e);
         tc_fence_after();
-        // three passes of 16 accumulator columns keep the register footprint small.  The first chain of an
-        // item in this CTA stores, later chains add with fire-and-forget red.global.add.f32: this thread is the
-        // only writer of its row and issues its updates in program order, so the sum order is fixed.
-#ifdef DFK_EXP_NODRAIN
-        if (false) {
-#else
-        if (valid > 0 || fresh) {
-#endif
+        const ChainRec rec = sm.chain[b];
+        float* P = partials + (size_t)rec.pslot * kTcPartialFloats;
+        // three passes of 16 accumulator columns keep the register footprint small.  The first chain of an item in
+        // this CTA stores, later chains add with fire-and-forget red.global.add.f32: this thread is the only writer
+        // of its row and issues its updates in program order, so the sum order is fixed.
+        if (rec.valid > 0 || rec.fresh) {
 #pragma unroll 1
           for (int pass = 0; pass < 3; ++pass) {
-            const int nq = pass < 2 ? 4 : (kTcCols - 32) / 4;  // float4 per pass (columns 40..47 are padding)
+            const int ncol = pass < 2 ? 16 : kTcCols - 32;  // columns 40..47 are padding
             uint32_t v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0u;
-            if (valid > 0) {
+            for (int c = 0; c < 16; ++c) v[c] = 0u;
+            if (rec.valid > 0) {
               tmem_ld_x16(lane_taddr + D_COL + NB * b + 16 * pass, v);
               tmem_wait_ld();
             }
-            // column-major partial: this lane's row at column j is P[j * kTcRowsPad + row] -> a warp writes 128
+            // column-major partial: this lane's row at column c is P[c * kTcRowsPad + row] -> a warp writes 128
             // contiguous bytes per column
             float* dcol = P + (16 * pass) * kTcRowsPad + row;
-            if (fresh) {
+            if (rec.fresh) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < 4 * nq) __stcg(dcol + j * kTcRowsPad, __uint_as_float(v[j]));
+              for (int c = 0; c < 16; ++c)
+                if (c < ncol) __stcg(dcol + c * kTcRowsPad, __uint_as_float(v[c]));
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < 4 * nq)
-                  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dcol + j * kTcRowsPad), "f"(__uint_as_float(v[j])) : "memory");
+              for (int c = 0; c < 16; ++c)
+                if (c < ncol)
+                  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dcol + c * kTcRowsPad), "f"(__uint_as_float(v[c])) : "memory");
             }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.d_empty[b]);
-        if (item_end && ow == 0 && lane == 0) reinterpret_cast<unsigned int*>(P)[kTcRowsPad * kTcCols] = inl;
-      };
-
-#ifdef DFK_TC_TIMERS
-      Tmr tm{0, dbg != 0 && warp == 8 && lane == 0};
-#else
-      Tmr tm{0, false};
-#endif
-      const bool is_a = (ogrp == 0);
-      unsigned long long t_ffull = 0, t_aempty = 0, t_build = 0, t_sync = 0, t_drain = 0, t_total = 0, t_misc = 0;
-#ifdef DFK_TC_TIMERS
-      const long long t_begin = tm.on ? clock64() : 0;
-#else
-      const long long t_begin = 0;
-#endif
-      for (int i = 0; i < ntiles; ++i) {
-        const int st = i % STAGES;
-        const int fb = i & 1;
-        tm.start();
-        mbar_wait(&sm.feat_full[fb], (i >> 1) & 1u);
-        tm.lap(t_ffull);
-        const TileMeta meta = sm.meta[fb];
-        const int tile_valid = meta.nv[0] + meta.nv[1] + meta.nv[2] + meta.nv[3];
-        if (is_a && ch.starts_chain(i, meta.item_changed)) {
-          if (i > 0) {
-            pend = true;
-            pend_e = ch.e;
-            pend_valid = chain_valid;
-            pend_item_end = meta.item_changed != 0;
-            pend_slot = cur_slot;
-            pend_fresh = slot_fresh;
-            pend_inliers = inliers;
-            slot_fresh = false;
-          }
-          ch.e += 1;
-          ch.tiles_in_chain = 0;
-          chain_valid = 0;
-          if (meta.item_changed) {
-            cur_slot = meta.slot;
-            slot_fresh = true;
-            inliers = 0;
-          }
-        }
-        ch.tiles_in_chain += 1;
-        chain_valid += tile_valid;
-        inliers += (unsigned)tile_valid;
-
-        // plain (non-volatile) shared-memory accesses: the compiler is free to overlap the loads of
-        // several chunks; the mbarrier waits / fences around the loops carry the "memory" clobbers
-        tm.lap(t_misc);
-        const float* __restrict__ vrow = sm.jc[st] + lane;  // compacted, pre-scaled rows: vrow[c * C]
-        const float4* __restrict__ featp = reinterpret_cast<const float4*>(sm.feat[fb]);
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const int nv = sm.meta[fb].nv[2 * h + ogrp];  // this group's block of the half (shared memory: no local-array indexing)
-          // A/B half h was last read by the MMAs of tile i-1
-          tm.start();
-          mbar_wait(&sm.a_empty[h], (i & 1u) ^ 1u);
-          tc_fence_after();
-          tm.lap(t_aempty);
-          unsigned char* bh = sm.B[h];
-          // each half = two 32-pixel blocks; operand group g builds block g of the half: 32 row loads, one
-          // 32-column tcgen05.st (registers -> TMEM lanes), and for the h rows the K-major B tile
-#ifdef DFK_EXP_NOOPBUILD
-          if (false) {
-#else
-          if (nv > 0) {
-#endif
-            const int c0 = HALF * h + 32 * ogrp;  // first compacted pixel of the block
-            const uint32_t a_taddr = lane_taddr + A_COL + c0;
-            uint32_t v[32];
-            if (ow < 2) {
-              const float* src = vrow + c0 * C;
-              float val[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) val[j] = src[j * C];
-              if (ow == 0) {
-                // B rows = features (this lane), 8 k-chunks of 4 pixels, 128 B apart
-                float4* brow = reinterpret_cast<float4*>(bh + (uint32_t)(lane >> 3) * B_SBO + (uint32_t)(lane & 7) * 16u) +
-                               8 * (8 * ogrp);
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  brow[8 * q] = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(val[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(val[j] - tf32_trunc(val[j]));
-              }
-            } else {
-              // pose / residual features: lanes 0-6 = h of feature 1+lane, lanes 7-13 = l of feature 1+(lane-7)
-              const int f = 1 + (lane < 7 ? lane : (lane < 14 ? lane - 7 : 0));
-              const float4* fp = featp + f * (FEAT_STRIDE / 4) + (c0 >> 2);
-              float4 x[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) x[q] = fp[q];
-              if (lane < 7) {
-                const uint32_t brow_i = 32u + (uint32_t)lane;
-                float4* brow = reinterpret_cast<float4*>(bh + (brow_i >> 3) * B_SBO + (brow_i & 7u) * 16u) + 8 * (8 * ogrp);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) brow[8 * q] = x[q];
-              }
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                float e0 = x[q].x, e1 = x[q].y, e2 = x[q].z, e3 = x[q].w;
-                if (lane >= 7) {
-                  e0 -= tf32_trunc(e0); e1 -= tf32_trunc(e1); e2 -= tf32_trunc(e2); e3 -= tf32_trunc(e3);
-                }
-                if (lane >= 14) { e0 = 0.f; e1 = 0.f; e2 = 0.f; e3 = 0.f; }
-                v[4 * q] = __float_as_uint(e0); v[4 * q + 1] = __float_as_uint(e1);
-                v[4 * q + 2] = __float_as_uint(e2); v[4 * q + 3] = __float_as_uint(e3);
-              }
-            }
-            tmem_st_x32(a_taddr, v);
-          }
-          tm.lap(t_build);
-          tmem_wait_st();
-          if (ow != 1) fence_proxy_async_smem();  // the code-l warp wrote TMEM only, no B rows
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.a_full[h]);
-          tm.lap(t_sync);
-        }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&sm.feat_empty[fb]);
-          mbar_arrive(&sm.stage_empty[st]);
-        }
-        tm.start();
-
-        if (is_a && pend) {  // the chain that ended before this tile: its MMAs completed long ago
-          drain(pend_e, pend_valid, pend_slot, pend_fresh, pend_item_end, pend_inliers);
-          pend = false;
-        }
-        tm.lap(t_drain);
-      }
-      if (is_a) drain(ch.e, chain_valid, cur_slot, slot_fresh, true, inliers);
-      if (tm.on) {
-        t_total = (unsigned long long)(clock64() - t_begin);
-        (void)t_begin;
-        atomicAdd(&g_dbg[6], t_ffull); atomicAdd(&g_dbg[7], t_aempty); atomicAdd(&g_dbg[8], t_build);
-        atomicAdd(&g_dbg[9], t_sync); atomicAdd(&g_dbg[10], t_drain); atomicAdd(&g_dbg[11], t_total);
-        atomicAdd(&g_dbg[12], (unsigned long long)ntiles); atomicAdd(&g_dbg[14], t_misc);
+        if (rec.item_end && ow == 0 && lane == 0) reinterpret_cast<unsigned int*>(P)[kTcRowsPad * kTcCols] = rec.inliers;
+        if (rec.last) break;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 11) tmem_dealloc(tbase, TMEM_COLS);
+  if (warp == 15) tmem_dealloc(tbase, TMEM_COLS);
 }
 
 }  // namespace
@@ -785,14 +538,14 @@ __global__ void sfm_ray_tables_kernel(const SfmItemDev* __restrict__ items, floa
 
 bool sfm_tc_supported(int code_size) { return code_size == 32; }
 
-size_t sfm_tc_smem_bytes() { return sizeof(Smem); }
+size_t sfm_tc_smem_bytes() { return sizeof(Smem) + 1024; }
 
 cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan, bool build_ray_tables,
                           float* partials_dev, cudaStream_t stream, cudaEvent_t ev_start, cudaEvent_t ev_stop)
 {
-  const size_t smem = sizeof(Smem);
+  const size_t smem = sizeof(Smem) + 1024;  // + the slack the kernel aligns the operand ring with
   static const cudaError_t attr_err =  // once per process, not once per launch
-      cudaFuncSetAttribute(sfm_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+      cudaFuncSetAttribute(sfm_step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Smem) + 1024));
   cudaError_t err = attr_err;
   if (err != cudaSuccess) return err;
   if (build_ray_tables) {  // only when the work list names a camera level the handle has no table for yet
@@ -800,27 +553,9 @@ cudaError_t launch_sfm_tc(const SfmItemDev* items_dev, const SfmLaunchPlan& plan
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
   }
-  static const int dbg = []() { const char* e = getenv("DFK_TC_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
-  if (dbg) {
-    unsigned long long z[16] = {0};
-    cudaMemcpyToSymbolAsync(g_dbg, z, sizeof(z), 0, cudaMemcpyHostToDevice, stream);
-  }
   if (ev_start) cudaEventRecord(ev_start, stream);
-  sfm_step_tc_kernel<<<plan.num_ctas, THREADS, smem, stream>>>(items_dev, plan.num_items, plan.num_tiles, partials_dev,
-                                                              dbg);
+  sfm_step_tc_kernel<<<plan.num_ctas, THREADS, smem, stream>>>(items_dev, plan.num_items, plan.num_tiles, partials_dev);
   if (ev_stop) cudaEventRecord(ev_stop, stream);
-  if (dbg) {
-    unsigned long long v[16];
-    cudaStreamSynchronize(stream);
-    cudaMemcpyFromSymbol(v, g_dbg, sizeof(v));
-    const double nt = v[12] ? (double)v[12] : 1.0;
-    fprintf(stderr,
-            "[dfk tc dbg] ctas=%d tiles=%d | per tile cycles: FE(g0+g1 thread0) tma_wait %.0f geom %.0f feat_empty_wait %.0f "
-            "write %.0f tma_issue %.0f | CTRL a_full_wait %.0f issue %.0f | OP feat_full_wait %.0f a_empty_wait %.0f build %.0f sync %.0f "
-            "drain %.0f misc %.0f total %.0f\n",
-            plan.num_ctas, plan.num_tiles, v[0] / nt, v[1] / nt, v[2] / nt, v[3] / nt, v[13] / nt, v[4] / nt, v[5] / nt, v[6] / nt,
-            v[7] / nt, v[8] / nt, v[9] / nt, v[10] / nt, v[14] / nt, v[11] / nt);
-  }
   return cudaGetLastError();
 }
 

@@ -87,6 +87,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_kmajor_noswizzle(uint32_t sme
          ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
+// MN-major ("transposed") 32-bit operands: instruction-descriptor bits, and the one canonical shared-memory layout the
+// hardware defines for them -- layout type 1 = SWIZZLE_128B_BASE32B (tools/umma_probe_mn.cu; SWIZZLE_NONE / _128B with
+// the MN-major bits set write zeros).  Atom = 32 elements along M/N x 4 along K (512 B, 512-byte aligned): K row r is
+// 128 contiguous bytes whose 32-byte chunk c sits at chunk position c ^ r.  `lbo` = byte distance between atoms
+// adjacent in M/N, `sbo` = between atoms adjacent in K (one K = 8 instruction spans two).
+constexpr uint32_t kIdescAMnMajor = 1u << 15;
+constexpr uint32_t kIdescBMnMajor = 1u << 16;
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
+{
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46) | (1ull << 61);
+}
+
 // ---------------------------------------------------------------------------------- MMA + commit
 // D[tmem] (+)= A[tmem] * B[smem]^T ; one elected thread issues.
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -99,6 +112,20 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; both operands through shared-memory descriptors
+__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             bool accumulate)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
 

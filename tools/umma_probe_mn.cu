@@ -36,6 +36,8 @@ struct Params {
   uint32_t ltype;     // descriptor layout type
   uint32_t idesc;
   int n;
+  uint32_t lbo_b;     // 0: B uses the A descriptor; else B's own LBO (B's n-th MN atom = feature atom n * lbo_b / lbo)
+  uint32_t base_off;  // byte offset of the tile inside the 1024-byte aligned window
 };
 
 __host__ __device__ inline uint32_t feat_addr(int layout, int f, int k)
@@ -43,6 +45,9 @@ __host__ __device__ inline uint32_t feat_addr(int layout, int f, int k)
   if (layout == 0) return (f / 32) * BLK_BYTES + k * 128 + ((((f % 32) / 4) ^ (k & 7)) * 16) + (f % 4) * 4;
   if (layout == 1) return (f / 4) * (KT * 16) + (k / 8) * 128 + (k % 8) * 16 + (f % 4) * 4;
   if (layout == 2) return (f / 8) * (KT * 32) + (k / 4) * 128 + (f % 8) * 16 + (k % 4) * 4;
+  // layout 4: MN-major SWIZZLE_128B_BASE32B (layout type 1): atoms of 32 features x 4 pixels (512 B): pixel k%4 = 128-byte
+  // row, 32-byte chunk (f%32)/8 of the row at position ((f%32)/8) ^ (k%4); K atoms 512 B apart, MN atoms BLK_BYTES apart
+  if (layout == 4) return (f / 32) * BLK_BYTES + (k / 4) * 512 + (k % 4) * 128 + ((((f % 32) / 8) ^ (k % 4)) * 32) + (f % 8) * 4;
   // layout 3: K-major SWIZZLE_128B, K blocks of 32 pixels: rows = features (128 B = 32 pixels), 8-row groups of 1024 B,
   // chunk (k%32)/4 of row f at position ((k%32)/4) ^ (f%8); K block q at q * KBLK3
   return (k / 32) * KBLK3 + (f / 8) * 1024 + (f % 8) * 128 + ((((k % 32) / 4) ^ (f % 8)) * 16) + (k % 4) * 4;
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ F,
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t s0 = smem_u32(smem);
-  const uint32_t sbase = (s0 + 1023u) & ~1023u;  // shared-window address, 1024-byte aligned
+  const uint32_t sbase = ((s0 + 1023u) & ~1023u) + P.base_off;  // shared-window address, 1024-byte aligned (+ offset)
 
   if (warp == 0) {
     tmem_alloc(&tmem_base_s, 64);
@@ -109,7 +114,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ F,
     for (int ks = 0; ks < KT / 8; ++ks) {
       const uint32_t start = (P.layout == 3) ? sbase + (ks / 4) * KBLK3 + (ks % 4) * 32 : sbase + ks * P.kstep;
       const uint64_t ad = make_desc(start, P.lbo, P.sbo, P.ltype);
-      umma_tf32_ss(tbase, ad, ad, P.idesc, ks > 0);  // B = the first N features of the same tile
+      const uint64_t bd = P.lbo_b ? make_desc(start, P.lbo_b, P.sbo, P.ltype) : ad;
+      umma_tf32_ss(tbase, ad, bd, P.idesc, ks > 0);  // B = the first N features of the same tile (or atoms 0, 2 with lbo_b = 2 lbo)
     }
     umma_commit(&bar);
   }
@@ -142,6 +148,13 @@ int main()
   srand(7);
   for (size_t i = 0; i < nf; ++i) hF[i] = (float)(rand() % 2001 - 1000) / 1000.0f;
   static double ref[M][NMAX];
+  static double ref2[M][NF];
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < NF; ++n) {
+      double s = 0;
+      for (int k = 0; k < KT; ++k) s += (double)tf32_trunc(hF[m * KT + k]) * (double)tf32_trunc(hF[n * KT + k]);
+      ref2[m][n] = s;
+    }
   for (int m = 0; m < M; ++m)
     for (int n = 0; n < NMAX; ++n) {
       double s = 0;
@@ -152,7 +165,7 @@ int main()
   cudaMalloc(&dF, nf * 4);
   cudaMalloc(&dD, M * NMAX * 4);
   cudaMemcpy(dF, hF, nf * 4, cudaMemcpyHostToDevice);
-  const size_t smem = TILE_BYTES + 2048;
+  const size_t smem = TILE_BYTES + 4096;
   cudaError_t e = cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) printf("attr: %s\n", cudaGetErrorString(e));
   const uint32_t MN = (1u << 15) | (1u << 16);
@@ -169,6 +182,15 @@ int main()
       {"K-major SW128 LBO=0 SBO=1024 N=48 (rows<80)", {3, 0, 1024, 0, 2, make_idesc_tf32(M, 48), 48}},
       {"K-major SW128 LBO=1024 SBO=1024 N=48", {3, 1024, 1024, 0, 2, make_idesc_tf32(M, 48), 48}},
       {"MN SW128 layout, K-major flags (control)", {0, BLK_BYTES, 1024, 1024, 2, make_idesc_tf32(M, 48), 48}},
+      {"MN SW128_32B LBO=blk SBO=512 N=64", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 64) | MN, 64}},
+      {"MN SW128_32B LBO=blk SBO=512 N=48", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 48) | MN, 48}},
+      {"MN SW128_32B LBO=blk SBO=512 N=32", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 32) | MN, 32}},
+      {"MN SW128_32B LBO=512 SBO=blk N=64", {4, 512, BLK_BYTES, 1024, 1, make_idesc_tf32(M, 64) | MN, 64}},
+      {"MN SW128_32B N=48, B atoms 0,2 (lbo_b=2blk)", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 48) | MN, 48, 2 * BLK_BYTES}},
+      {"MN SW128_32B N=64, B atoms 0,2 (lbo_b=2blk)", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 64) | MN, 64, 2 * BLK_BYTES}},
+      {"MN SW128_32B N=48 base+512", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 48) | MN, 48, 0, 512}},
+      {"MN SW128_32B N=48 base+128", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 48) | MN, 48, 0, 128}},
+      {"MN SW128_32B A only MN (B K-major flag)", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 48) | (1u << 15), 48}},
   };
   static float hD[M * NMAX];
   for (const Var& v : vars) {
@@ -183,7 +205,8 @@ int main()
     int sentinels = 0;
     for (int m = 0; m < (v.p.layout == 3 ? 80 : M); ++m)
       for (int n = 0; n < v.p.n; ++n) {
-        const double d = fabs((double)hD[m * NMAX + n] - ref[m][n]);
+        const int nb = (v.p.lbo_b && n >= 32) ? n + 32 : n;  // B atom 1 = feature atom 2
+        const double d = fabs((double)hD[m * NMAX + n] - ref2[m][nb]);
         if (hD[m * NMAX + n] == 7.0f) ++sentinels;
         if (d > err_all) err_all = d;
         if (n < 32 && d > err_32) err_32 = d;

@@ -61,7 +61,7 @@ constexpr int TILE = kTcTilePixels;  // 128
 constexpr int NFE = 12;              // front-end warps
 constexpr int THREADS = 512;         // 12 front-end warps, 3 drain warps, control
 #ifndef DFK_TC_SLOTS
-#define DFK_TC_SLOTS 8
+#define DFK_TC_SLOTS 6
 #endif
 constexpr int NSLOT = DFK_TC_SLOTS;  // operand slots; block j uses slot j % NSLOT
 constexpr uint32_t ATOM_BYTES = 512;              // 32 features x 4 pixels
@@ -192,7 +192,9 @@ __device__ __noinline__ void wd_wait(uint64_t* bar, uint32_t parity, int what, i
 
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d)
 {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+  // no "memory" clobber: the front-end's only plain shared-memory accesses are reads of its item copy and the slot
+  // meta (written after the proxy fence, which does carry the clobber); volatile keeps the stores ordered with the fence
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
 }
 
 // 16 bytes of a code-Jacobian row; rows of items without the BULK flag are only 4-byte aligned
@@ -293,11 +295,14 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           pxx -= W;
           ++py;
         }
+        const float* __restrict__ jac = I.jac;
         const uint32_t joff = py * I.jac_pitch + pxx * C;  // this pixel's code-Jacobian row (floats)
         float feat[8];
         bool ok = false;
         if (blk_live) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(I.jac + joff));
+#ifndef DFK_TC_NOPREFETCH
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(jac + joff));
+#endif
           const float xn = __ldg(I.ray_tab + pxx);
           const float yn = __ldg(I.ray_tab + W + py);
           float d = __ldg(I.dpt0 + (size_t)py * I.dpt0_pitch + pxx);
@@ -311,7 +316,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
 #pragma unroll
             for (int i8 = 0; i8 < 8; ++i8) {
               const uint32_t offk = __shfl_sync(0xffffffffu, joff, 4 * i8 + (lane >> 3));
-              float p = chunk_dot(load_chunk(I.jac + offk + 4 * (lane & 7), a16), cc);
+              float p = chunk_dot(load_chunk(jac + offk + 4 * (lane & 7), a16), cc);
               p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 4));
               p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 2));
               p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 1));
@@ -329,6 +334,10 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
               int ix, iy;
               float fu, fv, gx, gy;
               bilin_setup(w.u, w.v, ix, iy, fu, fv);
+#ifdef DFK_EXP_NOGATHER  // experiment (wrong results): sample at the pixel itself -> coalesced taps
+              ix = (int)pxx < (int)W - 1 ? (int)pxx : (int)W - 2;
+              iy = (int)py < (int)I.height - 1 ? (int)py : (int)I.height - 2;
+#endif
               sample_grad(I.grad1, I.grad1_pitch, true, ix, iy, fu, fv, gx, gy);  // the API guarantees 8-byte rows here
               const float i1 = sample_scalar(I.img1, I.img1_pitch, ix, iy, fu, fv);
               float a[6], c00, c02, c11, c12;
@@ -370,7 +379,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
             const int kp = 4 * i8 + r;
             const uint32_t offk = __shfl_sync(0xffffffffu, joff, kp);
             v[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((bal >> kp) & 1u) v[i8] = load_chunk(I.jac + offk + 4 * (lane & 7), a16);
+#ifdef DFK_EXP_NOJC  // experiment (wrong results): no code-Jacobian traffic
+            if ((bal >> kp) & 1u) v[i8] = make_float4(0.1f * (float)offk, 0.2f, 0.3f, 0.4f);
+#else
+            if ((bal >> kp) & 1u) v[i8] = load_chunk(jac + offk + 4 * (lane & 7), a16);
+#endif
           }
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
@@ -378,21 +391,30 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
             if ((mask >> (i8 >> 1)) & 1) {
               const float h0 = sk * v[i8].x, h1 = sk * v[i8].y, h2 = sk * v[i8].z, h3 = sk * v[i8].w;
               const uint32_t dst = dst0 + (uint32_t)i8 * ATOM_BYTES;
+#ifdef DFK_EXP_NOSTORE  // experiment (wrong results): one store instead of two
+              sts128(dst, h0 + tf32_trunc(h1), h1, h2 - tf32_trunc(h3), h3);
+#else
               sts128(dst, h0, h1, h2, h3);  // the tensor core truncates: h rows carry the raw values
               sts128(dst + MN_STRIDE, h0 - tf32_trunc(h0), h1 - tf32_trunc(h1), h2 - tf32_trunc(h2), h3 - tf32_trunc(h3));
+#endif
             }
           }
-          // pose atom: this thread's pixel = K position `lane`: h of the 7 pose / residual values in chunk 0, l in chunk 1
+          // pose atom: this thread's pixel = K position `lane`: h of the 7 pose / residual values in chunk 0, l in chunk 1.
+          // Lanes of odd K atoms write the two 16-byte halves of a chunk in the opposite order: the 8 lanes of a
+          // quarter warp (two K atoms x four rows) then hit 8 different bank groups
           {
             const int rp = lane & 3;
+            const bool odd = (lane & 4) != 0;
             const uint32_t row = sbase + 2u * MN_STRIDE + (uint32_t)(lane >> 2) * ATOM_BYTES + (uint32_t)rp * 128u;
-            const uint32_t ch = row + ((uint32_t)rp << 5);         // chunk 0 ^ rp
-            const uint32_t cl = row + ((uint32_t)(rp ^ 1) << 5);   // chunk 1 ^ rp
-            sts128(ch, feat[1], feat[2], feat[3], feat[4]);
-            sts128(ch + 16u, feat[5], feat[6], feat[7], 0.0f);
-            sts128(cl, feat[1] - tf32_trunc(feat[1]), feat[2] - tf32_trunc(feat[2]), feat[3] - tf32_trunc(feat[3]),
-                   feat[4] - tf32_trunc(feat[4]));
-            sts128(cl + 16u, feat[5] - tf32_trunc(feat[5]), feat[6] - tf32_trunc(feat[6]), feat[7] - tf32_trunc(feat[7]), 0.0f);
+            const uint32_t ch = row + ((uint32_t)rp << 5) + (odd ? 16u : 0u);         // chunk 0 ^ rp
+            const uint32_t cl = row + ((uint32_t)(rp ^ 1) << 5) + (odd ? 16u : 0u);   // chunk 1 ^ rp
+            const float a0 = feat[1], a1 = feat[2], a2 = feat[3], a3 = feat[4], b0 = feat[5], b1 = feat[6], b2 = feat[7];
+            const float la0 = a0 - tf32_trunc(a0), la1 = a1 - tf32_trunc(a1), la2 = a2 - tf32_trunc(a2), la3 = a3 - tf32_trunc(a3);
+            const float lb0 = b0 - tf32_trunc(b0), lb1 = b1 - tf32_trunc(b1), lb2 = b2 - tf32_trunc(b2);
+            sts128(ch, odd ? b0 : a0, odd ? b1 : a1, odd ? b2 : a2, odd ? 0.0f : a3);
+            sts128(ch ^ 16u, odd ? a0 : b0, odd ? a1 : b1, odd ? a2 : b2, odd ? a3 : 0.0f);
+            sts128(cl, odd ? lb0 : la0, odd ? lb1 : la1, odd ? lb2 : la2, odd ? 0.0f : la3);
+            sts128(cl ^ 16u, odd ? la0 : lb0, odd ? la1 : lb1, odd ? la2 : lb2, odd ? la3 : 0.0f);
           }
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA's operand fetch
         }
@@ -407,66 +429,92 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       }
     } else if (warp == 15) {
       // ======================================================================= control warp
-      if (lane == 0) {
+      // The whole warp walks the blocks (uniform control flow: waits, meta, chain bookkeeping are done redundantly by all
+      // lanes, which keeps the loop free of divergence); one elected lane issues the MMAs, the commits and the records.
+      // This loop is serial per CTA, so its length bounds the kernel: counters instead of divisions, descriptors advanced
+      // by constants, one 16-byte load for the slot meta.
+      {
+        const bool leader = elect_one_sync();
         const uint32_t idesc = make_idesc_tf32(MM, NB) | kIdescAMnMajor | kIdescBMnMajor;
+        const uint32_t desc_hi = (ATOM_BYTES >> 4) | (1u << 14) | (1u << 29);  // SBO | version 1 | SWIZZLE_128B_BASE32B
+        const uint32_t ring_lo = (smem_u32(&sm.op[0][0]) & 0x3ffffu) >> 4;
         int e = -1, tiles_in_chain = 0;
-        bool first = true;
+        uint32_t first = 1;
         int chain_valid = 0, cur_pslot = -1;
         bool slot_fresh = true;
         unsigned int inliers = 0;
         // close chain e: publish its record, then let the drain warps go once its MMAs have completed
         auto close_chain = [&](bool item_end, bool last) {
-          ChainRec& r = sm.chain[e & 1];
-          r.valid = chain_valid;
-          r.pslot = cur_pslot;
-          r.fresh = slot_fresh ? 1 : 0;
-          r.item_end = item_end ? 1 : 0;
-          r.inliers = inliers;
-          r.last = last ? 1 : 0;
+          if (leader) {
+            ChainRec& r = sm.chain[e & 1];
+            r.valid = chain_valid;
+            r.pslot = cur_pslot;
+            r.fresh = slot_fresh ? 1 : 0;
+            r.item_end = item_end ? 1 : 0;
+            r.inliers = inliers;
+            r.last = last ? 1 : 0;
+            umma_commit(&sm.d_full[e & 1]);
+            mbar_arrive(&sm.d_full[e & 1]);
+          }
           slot_fresh = false;
-          umma_commit(&sm.d_full[e & 1]);
-          mbar_arrive(&sm.d_full[e & 1]);
         };
+        int slot = 0, next_w = NSLOT % NFE;
+        uint32_t full_phase = 0;
         for (int j = 0; j < nblocks; ++j) {
-          const int slot = j % NSLOT;
-          TC_WAIT(&sm.full[slot], (uint32_t)(j / NSLOT) & 1u, 1, j);
+          TC_WAIT(&sm.full[slot], full_phase, 1, j);
           tc_fence_after();
-          const SlotMeta meta = sm.meta[slot];
+          const int4 meta = *reinterpret_cast<const int4*>(&sm.meta[slot]);  // mask, nvalid, item_changed, pslot
           if ((j & 3) == 0) {
-            if (j == 0 || meta.item_changed != 0 || tiles_in_chain == kFlushTiles) {
-              if (j > 0) close_chain(meta.item_changed != 0, false);
+            if (j == 0 || meta.z != 0 || tiles_in_chain == kFlushTiles) {
+              if (j > 0) close_chain(meta.z != 0, false);
               e += 1;
               tiles_in_chain = 0;
               chain_valid = 0;
-              first = true;
+              first = 1;
               const int use = e >> 1;  // n-th use of this accumulator buffer (and of its record)
               if (use >= 1) {
                 TC_WAIT(&sm.d_empty[e & 1], (uint32_t)(use - 1) & 1u, 2, e);
                 tc_fence_after();
               }
-              if (j == 0 || meta.item_changed != 0) {
-                cur_pslot = meta.pslot;
+              if (j == 0 || meta.z != 0) {
+                cur_pslot = meta.w;
                 slot_fresh = true;
                 inliers = 0;
               }
             }
             tiles_in_chain += 1;
           }
-          chain_valid += meta.nvalid;
-          inliers += (unsigned)meta.nvalid;
-          const uint32_t d_addr = tbase + D_COL + NB * (uint32_t)(e & 1);
-          const uint32_t sbase = smem_u32(&sm.op[slot][0]);
-          const uint64_t adesc = make_smem_desc_mn_sw128_32b(sbase, MN_STRIDE, ATOM_BYTES);
-          const uint64_t bdesc = make_smem_desc_mn_sw128_32b(sbase, 2 * MN_STRIDE, ATOM_BYTES);
+          chain_valid += meta.y;
+          inliers += (unsigned)meta.y;
+          if (leader) {
+            const uint32_t d_addr = tbase + D_COL + NB * (uint32_t)(e & 1);
+            const uint32_t lo = ring_lo + (uint32_t)slot * (SLOT_BYTES >> 4);
+            if (meta.x == 15) {  // the common case: four k-steps back to back
+              umma_tf32_ss_x4(d_addr, lo | ((MN_STRIDE >> 4) << 16), lo | ((2 * MN_STRIDE >> 4) << 16), desc_hi, idesc, first ^ 1u,
+                              (2 * ATOM_BYTES) >> 4);
+              first = 0;
+            } else {
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            if ((meta.mask >> gq) & 1) {
-              const uint64_t adv = (uint64_t)((2u * ATOM_BYTES * (uint32_t)gq) >> 4);  // two K atoms per k-step
-              umma_tf32_ss(d_addr, adesc + adv, bdesc + adv, idesc, !first);
-              first = false;
+              for (int gq = 0; gq < 4; ++gq) {
+                if ((meta.x >> gq) & 1) {
+                  const uint32_t adv = (uint32_t)gq * ((2 * ATOM_BYTES) >> 4);  // two K atoms per k-step
+#ifndef DFK_EXP_NOMMA  // experiment (wrong results): no tensor-core work, no operand fetch
+                  umma_tf32_ss(d_addr, ((uint64_t)desc_hi << 32) | (lo + adv) | ((MN_STRIDE >> 4) << 16),
+                               ((uint64_t)desc_hi << 32) | (lo + adv) | ((2 * MN_STRIDE >> 4) << 16), idesc, first == 0);
+#endif
+                  first = 0;
+                }
+              }
             }
+            umma_commit(&sm.done[next_w]);  // the slot's next user: block j + NSLOT
+          } else if (meta.x != 0) {
+            first = 0;
           }
-          umma_commit(&sm.done[(j + NSLOT) % NFE]);  // the slot's next user: block j + NSLOT
+          if (++slot == NSLOT) {
+            slot = 0;
+            full_phase ^= 1u;
+          }
+          if (++next_w == NFE) next_w = 0;
         }
         close_chain(true, true);
       }

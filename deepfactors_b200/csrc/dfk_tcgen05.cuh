@@ -129,6 +129,48 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
       : "memory");
 }
 
+// four k-steps of one operand block: descriptors {a_lo | hi}, {b_lo | hi}, start addresses advanced by `step` (16-byte
+// units) per k-step; the first MMA accumulates iff `accumulate`, the rest always
+__device__ __forceinline__ void umma_tf32_ss_x4(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t step)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, t;\n\t"
+      ".reg .b64 a, b, s;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 a, {%1, %3};\n\t"
+      "mov.b64 b, {%2, %3};\n\t"
+      "cvt.u64.u32 s, %6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %4, p;\n\t"
+      "add.u64 a, a, s;\n\t"
+      "add.u64 b, b, s;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %4, t;\n\t"
+      "add.u64 a, a, s;\n\t"
+      "add.u64 b, b, s;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %4, t;\n\t"
+      "add.u64 a, a, s;\n\t"
+      "add.u64 b, b, s;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], a, b, %4, t;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate), "r"(step)
+      : "memory");
+}
+
+__device__ __forceinline__ bool elect_one_sync()
+{
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // arrives (count 1) on `bar` when every tcgen05 operation this thread issued so far has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {

@@ -24,7 +24,7 @@
 
 using namespace dfk;
 
-constexpr int M = 128, NF = 128, KT = 64, NMAX = 64;
+constexpr int M = 128, NF = 128, KT = 64, NMAX = 96;
 constexpr uint32_t BLK_BYTES = KT * 128;
 constexpr uint32_t TILE_BYTES = NF * KT * 4;
 constexpr uint32_t KBLK3 = 80 * 128;  // rows 80..127 of a K block overlap the next block (junk rows of D)
@@ -38,6 +38,7 @@ struct Params {
   int n;
   uint32_t lbo_b;     // 0: B uses the A descriptor; else B's own LBO (B's n-th MN atom = feature atom n * lbo_b / lbo)
   uint32_t base_off;  // byte offset of the tile inside the 1024-byte aligned window
+  int m64;            // 1: M = 64 with A = feature atoms 0 and 2 (rows 0-31 = features 0-31, rows 32-63 = features 64-95)
 };
 
 __host__ __device__ inline uint32_t feat_addr(int layout, int f, int k)
@@ -59,17 +60,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
          ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 
-__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc)
-{
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
-      : "memory");
-}
 
 // F: [NF][KT]
 __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ F, float* __restrict__ D, Params P)
@@ -82,7 +72,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ F,
   const uint32_t sbase = ((s0 + 1023u) & ~1023u) + P.base_off;  // shared-window address, 1024-byte aligned (+ offset)
 
   if (warp == 0) {
-    tmem_alloc(&tmem_base_s, 64);
+    tmem_alloc(&tmem_base_s, 128);
     tmem_relinquish();
   }
   if (tid == 0) {
@@ -129,7 +119,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ F,
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, 64);
+  if (warp == 0) tmem_dealloc(tbase, 128);
 }
 
 static float tf32_trunc(float x)
@@ -190,6 +180,7 @@ int main()
       {"MN SW128_32B N=64, B atoms 0,2 (lbo_b=2blk)", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 64) | MN, 64, 2 * BLK_BYTES}},
       {"MN SW128_32B N=48 base+512", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 48) | MN, 48, 0, 512}},
       {"MN SW128_32B N=48 base+128", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 48) | MN, 48, 0, 128}},
+      {"MN SW128_32B M=64 A atoms 0,2  N=80 B atoms 0,1,2", {4, 2 * BLK_BYTES, 512, 1024, 1, make_idesc_tf32(64, 80) | MN, 80, BLK_BYTES, 0, 1}},
       {"MN SW128_32B A only MN (B K-major flag)", {4, BLK_BYTES, 512, 1024, 1, make_idesc_tf32(M, 48) | (1u << 15), 48}},
   };
   static float hD[M * NMAX];
@@ -212,6 +203,21 @@ int main()
         if (n < 32 && d > err_32) err_32 = d;
         if (n < 32 && m < 32 && d > err_r32) err_r32 = d;
       }
+    if (v.p.m64) {  // where did the 64 rows go?  match every TMEM lane against the reference rows
+      printf("%-44s lane -> A row:", v.name);
+      for (int lane = 0; lane < 128; ++lane) {
+        int best = -1;
+        for (int r = 0; r < 64 && best < 0; ++r) {
+          const int fa = r < 32 ? r : 32 + r;
+          double e = 0;
+          for (int n = 0; n < v.p.n; ++n) e = fmax(e, fabs((double)hD[lane * NMAX + n] - ref2[fa][n]));
+          if (e < 1e-4) best = r;
+        }
+        if (best >= 0 && (lane % 16 == 0 || best % 16 != lane % 16)) printf(" %d:%d", lane, best);
+      }
+      printf("\n");
+      continue;
+    }
     printf("%-44s err all=%.2e cols<32=%.2e 32x32=%.2e untouched=%d  D00=%.4f/%.4f D[1][0]=%.4f/%.4f D[40][35]=%.4f/%.4f D[70][5]=%.4f/%.4f\n",
            v.name, err_all, err_32, err_r32, sentinels, hD[0], ref[0][0], hD[NMAX], ref[1][0], hD[40 * NMAX + 35],
            ref[40][35], hD[70 * NMAX + 5], ref[70][5]);

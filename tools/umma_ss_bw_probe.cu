@@ -21,17 +21,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
   return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
-__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc)
-{
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
-      : "memory");
-}
 
 // mode bit 0: MMAs, bit 1: LSU traffic.  a_in_tmem: use the TS form (A from TMEM columns 64..) for comparison
-__global__ void __launch_bounds__(128 + 32 * NW) bw_kernel(int mode, int nmma, int m_rows, int n_cols, int a_in_tmem,
+__global__ void __launch_bounds__(128 + 32 * NW) bw_kernel(int mode, int nmma, int m_rows, int n_cols, int a_in_tmem, int nacc,
                                                            unsigned long long* out)
 {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -69,11 +61,11 @@ __global__ void __launch_bounds__(128 + 32 * NW) bw_kernel(int mode, int nmma, i
         if (a_in_tmem) {
           asm volatile(
               "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tbase),
-              "r"(tbase + 64 + 8 * (i & 7)), "l"(bd), "r"(idesc), "r"((uint32_t)(i > 0))
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tbase + 48 * (uint32_t)(i % nacc)),
+              "r"(tbase + 192 + 8 * (i & 7)), "l"(bd), "r"(idesc), "r"((uint32_t)(i >= nacc))
               : "memory");
         } else {
-          umma_tf32_ss(tbase, ad, bd, idesc, i > 0);
+          umma_tf32_ss(tbase + 48 * (uint32_t)(i % nacc), ad, bd, idesc, i >= nacc);
         }
       }
       umma_commit(&bar);
@@ -124,20 +116,20 @@ int main()
   const size_t smem = 49152 + NW * 4096 + 2048;
   cudaFuncSetAttribute(bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int nmma = 20000;
-  struct Cfg { const char* name; int mode, m, n, ts; } cfgs[] = {
-      {"SS M128 N48 alone", 1, 128, 48, 0},       {"SS M128 N48 + LSU", 3, 128, 48, 0},
-      {"SS M128 N64 alone", 1, 128, 64, 0},       {"SS M64  N48 alone", 1, 64, 48, 0},
-      {"SS M64  N80 alone", 1, 64, 80, 0},        {"TS M128 N48 alone", 1, 128, 48, 1},
-      {"TS M128 N48 + LSU", 3, 128, 48, 1},       {"LSU alone", 2, 128, 48, 0},
+  struct Cfg { const char* name; int mode, m, n, ts, nacc; } cfgs[] = {
+      {"SS M128 N48 1 acc", 1, 128, 48, 0, 1}, {"SS M128 N48 2 acc", 1, 128, 48, 0, 2}, {"SS M128 N48 4 acc", 1, 128, 48, 0, 4},
+      {"SS M64 N80 1 acc(80 cols!)", 1, 64, 80, 0, 1}, {"SS M64 N48 2 acc", 1, 64, 48, 0, 2}, {"SS M64 N48 4 acc", 1, 64, 48, 0, 4},
+      {"TS M128 N48 1 acc", 1, 128, 48, 1, 1}, {"TS M128 N48 2 acc", 1, 128, 48, 1, 2}, {"TS M128 N48 4 acc", 1, 128, 48, 1, 4},
+      {"SS M128 N48 4 acc + LSU", 3, 128, 48, 0, 4}, {"LSU alone", 2, 128, 48, 0, 1},
   };
   for (const Cfg& c : cfgs) {
     unsigned long long h[8] = {0};
     cudaMemset(d, 0, 64);
-    bw_kernel<<<sms, 128 + 32 * NW, smem>>>(c.mode, nmma, c.m, c.n, c.ts, d);
+    bw_kernel<<<sms, 128 + 32 * NW, smem>>>(c.mode, nmma, c.m, c.n, c.ts, c.nacc, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("%s: %s\n", c.name, cudaGetErrorString(e)); return 1; }
     cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
-    printf("%-22s", c.name);
+    printf("%-30s", c.name);
     if (c.mode & 1) printf(" %.1f cycles / MMA", (double)h[0] / nmma);
     if (c.mode & 2) printf("  LSU: %.1f B/cycle/SM (%d warps, %.0f cycles)", (double)h[2] * 512.0 * NW / (double)h[1], NW, (double)h[1]);
     printf("\n");

@@ -61,7 +61,7 @@ constexpr int TILE = kTcTilePixels;  // 128
 constexpr int NFE = 12;              // front-end warps
 constexpr int THREADS = 512;         // 12 front-end warps, 3 drain warps, control
 #ifndef DFK_TC_SLOTS
-#define DFK_TC_SLOTS 6
+#define DFK_TC_SLOTS 7
 #endif
 constexpr int NSLOT = DFK_TC_SLOTS;  // operand slots; block j uses slot j % NSLOT
 constexpr uint32_t ATOM_BYTES = 512;              // 32 features x 4 pixels
@@ -122,8 +122,8 @@ struct Smem {
   uint64_t done[NFE];
   uint64_t d_full[2];
   uint64_t d_empty[2];
-  SlotMeta meta[NSLOT];
-  ChainRec chain[2];
+  alignas(16) SlotMeta meta[NSLOT];  // read with one 16-byte load
+  alignas(16) ChainRec chain[2];
   uint32_t tmem_base;
 };
 static_assert(sizeof(ItemSmem) * NFE >= MN_STRIDE, "the ring's tail pad");
@@ -435,7 +435,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       // by constants, one 16-byte load for the slot meta.
       {
         const bool leader = elect_one_sync();
+#ifdef DFK_EXP_SMALLMMA  // experiment (wrong results): same issue pattern, a fraction of the operand fetch
+        const uint32_t idesc = make_idesc_tf32(64, 16) | kIdescAMnMajor | kIdescBMnMajor;
+#else
         const uint32_t idesc = make_idesc_tf32(MM, NB) | kIdescAMnMajor | kIdescBMnMajor;
+#endif
         const uint32_t desc_hi = (ATOM_BYTES >> 4) | (1u << 14) | (1u << 29);  // SBO | version 1 | SWIZZLE_128B_BASE32B
         const uint32_t ring_lo = (smem_u32(&sm.op[0][0]) & 0x3ffffu) >> 4;
         int e = -1, tiles_in_chain = 0;

@@ -158,6 +158,43 @@ __device__ __forceinline__ void umma_tf32_ss_x4(uint32_t d_tmem, uint32_t a_lo, 
       : "memory");
 }
 
+// kind::f16 with bf16 inputs, fp32 accumulate:  [4,6) c = F32 (1) | [7,10) a = BF16 (1) | [10,13) b = BF16 (1) | N >> 3 | M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N)
+{
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// two k-steps of one operand block, A and B through the same descriptor {lo | hi}, start advanced by `step` (16-byte
+// units); the first MMA accumulates iff `accumulate`, the second always
+__device__ __forceinline__ void umma_bf16_ss_x2(uint32_t d_tmem, uint32_t lo, uint32_t hi, uint32_t idesc, uint32_t accumulate,
+                                                uint32_t step)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, t;\n\t"
+      ".reg .b64 a, s;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 a, {%1, %2};\n\t"
+      "cvt.u64.u32 s, %5;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, a, %3, p;\n\t"
+      "add.u64 a, a, s;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, a, %3, t;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(lo), "r"(hi), "r"(idesc), "r"(accumulate), "r"(step)
+      : "memory");
+}
+
 __device__ __forceinline__ bool elect_one_sync()
 {
   uint32_t pred;

@@ -1,47 +1,61 @@
+// ARCHIVED EXPERIMENT (round 2) -- not built.  Three-term bf16 split ([h;m;l] x [h;m], kind::f16, K = 16, MN-major
+// SWIZZLE_128B operands) of the direct-operand kernel.  Parity-green (max rel. error of JtJ vs fp64 2.0e-6, inliers exact,
+// 30/30 sfm GPU tests) but SLOWER than the production tf32 [h;l] x h version: 0.212 ms vs 0.148 ms on the pair8 batch.
+// ncu (profiles/README.md, round 2): +22 % executed instructions (the 3-way split costs ~5.5 instructions per value
+// against 2), the front-end no longer fits its 64-register cap (ptxas ignores setmaxnreg when allocating: 56-208 bytes
+// of spills = 2.4 M local-memory requests per launch, which eat the shared-memory wavefronts the smaller operands
+// save), one front-end warp less (the 120 accumulator rows need a fourth drain warp), and 2.7 x larger partials
+// (128 x 80 accumulator).  With the MMAs removed it still takes 0.207 ms, i.e. the loss is in the front-end.
+// It needs kTcRows = 120, kTcCols = 80, kTcRowsPad = 128 in dfk_internal.h and the 8-term finalize
+// G = hh + (hm + mh) + mm + (lh + lh^T) + (lm + lm^T) with the feature-slot maps given in the header comment below.
 // dfk_sfm_tc.cu -- SfmAligner::RunStep hot path, tcgen05 tensor-core Gram variant (sm_100a, C = 32).
 //
 // Same contract as dfk_sfm_fp32.cu (replaces kernel_step_calculate + DenseSfm + the two-kernel
 // reduction of sources/cuda/cu_sfmaligner.cpp:40-70,149-185, dense_sfm.h:133-201), different engine
 // for the reduced Gram  G = sum_p m_p^T m_p,  m = w*[ e*jc (32) | a (6) | diff (1) ]  (39 features):
 //
-//   Split precision ("3xTF32" folded into ONE MMA): every feature value v is split exactly into
-//   h = the bits the tensor core keeps (fp32 -> tf32 is a truncation of the low 13 mantissa bits on
-//   this hardware, measured by tools/umma_probe.cu) and l = v - h.  With A = [h rows ; l rows] and B = h,
-//   one tcgen05.mma.kind::tf32 per 8 pixels yields HH = sum h h^T and LH = sum l h^T;
-//   G = HH + LH + LH^T  drops only the l*l terms (~2^-22).
+//   Split precision, three bf16 terms folded into ONE MMA: every feature value v is split exactly into
+//   h = bf16(v), m = bf16(v - h), l = bf16(v - h - m)  (8 + 8 + 8 mantissa bits; the two subtractions are exact in fp32).
+//   With A = [h ; m ; l] (120 of M = 128 rows) and B = [h ; m] (80 columns), one tcgen05.mma.kind::f16 per 16 pixels
+//   yields hh, hm, mh, mm, lh, lm in fp32;  G = hh + hm + mh + mm + (lh + lh^T) + (lm + lm^T)  drops only the m*l and
+//   l*l terms (~2^-24).  Against the round-1 tf32 split ([h;l] x h, 4-byte operands, K = 8) this halves the number of
+//   MMAs and cuts the operand bytes the tensor core fetches from shared memory from 22 KB to 13 KB per 32 pixels, and
+//   the operand stores from 10 KB to 8 KB -- the kernel is bound by the SM's shared-memory / L1 data path, which the
+//   operand fetch shares with the front-end's loads and stores (tools/umma_ss_bw_probe.cu).
 //
-//   Round-2 data path ("direct operands"): both MMA operands are read from shared memory in the PIXEL-major
-//   ("MN-major") layout a per-pixel front-end writes naturally -- canonical layout SWIZZLE_128B_BASE32B, the one the
-//   hardware defines for transposed 32-bit operands (tools/umma_probe_mn.cu: atoms of 32 features x 4 pixels, the
-//   32-byte chunk c of pixel row r stored at chunk position c ^ r).  There is no operand-building stage, no TMEM A
-//   operand, no transposition and no tile staging any more: a front-end warp goes from global memory to a finished
-//   operand block on its own and hands it to the MMA issuer with one mbarrier arrival.
+//   Data path ("direct operands"): both MMA operands are read from shared memory in the PIXEL-major ("MN-major")
+//   layout a per-pixel front-end writes naturally -- canonical SWIZZLE_128B, atoms of 64 features x 8 pixels (1 KB): pixel
+//   row r = 128 contiguous bytes whose 16-byte chunk c is stored at chunk position c ^ r (tools/umma_probe_bf16mn.cu).
+//   There is no operand-building stage, no TMEM A operand, no transposition and no tile staging: a front-end warp goes
+//   from global memory to a finished operand block on its own and hands it to the MMA issuer with one mbarrier arrival.
 //
-//   Per CTA (512 threads, 2 CTAs / SM, 128 TMEM columns each; register budgets by setmaxnreg):
-//     warps 0-11  front-end : warp w owns the CTA's 32-pixel blocks j = w, w+12, ... (a 128-pixel tile = 4 blocks).
+//   Per CTA (512 threads, 2 CTAs / SM, 256 TMEM columns each; register budgets by setmaxnreg):
+//     warps 0-10  front-end : warp w owns the CTA's 32-pixel blocks j = w, w+11, ... (a 128-pixel tile = 4 blocks).
 //                             One thread per pixel: (optional depth decode,) exact-order validity chain, bilinear
 //                             gathers, Jacobian row, Huber -> s = w*e, w*a[6], w*diff.  Then the block's code-Jacobian
-//                             rows are read straight from global memory, COALESCED (lane = 16-byte chunk lane&7 of pixel
-//                             4i + lane/8; the rows were prefetched into L2 when the block started), scaled by the
-//                             pixel's s (one shuffle), split into h / l and stored as the code-h and code-l atoms of
-//                             an operand slot; each thread adds its own pixel's 7 pose/residual values (h and l) to the
-//                             third atom.  Invalid pixels contribute exact zeros; 8-pixel groups without a valid
-//                             pixel are skipped altogether (no loads, no MMA).
-//     warps 12-14 drain     : pull a finished accumulation chain out of TMEM (tcgen05.ld) and add it in round-to-nearest
+//                             rows are read straight from global memory, COALESCED (8 lanes = the eight 16-byte chunks of
+//                             one pixel, 4 pixels per instruction; the rows were prefetched into L2 when the block
+//                             started), scaled by the pixel's s (one shuffle), split into h / m / l and stored into the
+//                             operand slot; each thread adds its own pixel's 7 pose/residual values.  Invalid pixels
+//                             contribute exact zeros; 16-pixel groups without a valid pixel are skipped (no loads, no MMA).
+//     warp 11     control   : walks the blocks in order: waits for the slot, issues one MMA per non-empty 16-pixel group
+//                             (A = the slot's two atoms: M = 128; B = atom 0 and the first 16 features of atom 1: N = 80),
+//                             commits the slot back to its next user, cuts the chains and publishes their records to the
+//                             drain warps.  It also allocates TMEM.
+//     warps 12-15 drain     : pull a finished accumulation chain out of TMEM (tcgen05.ld) and add it in round-to-nearest
 //                             fp32 to the CTA's partial in global memory (single writer per address, program order).
-//     warp 15     control   : lane 0 walks the blocks in order: waits for the slot, issues one MMA per non-empty
-//                             8-pixel group (A = the slot's atoms 0,1,2 (+1 junk atom: M = 128), B = atoms 0 and 2:
-//                             N = 48), commits the slot back to the front-end, cuts the chains and publishes their
-//                             records to the drain warps.  It also allocates TMEM.
-//   Operand slot (12 KB): atom a (a = 0 code-h, 1 code-l, 2 pose: h at features 0-7, l at 8-15, rest zero) at
-//   a * 4096; inside, K atom q (pixels 4q..4q+3) at q * 512, pixel row r at r * 128, 32-byte chunk c at (c ^ r) * 32.
-//   Accumulator rows (TMEM lanes): 0-31 code-h, 32-63 code-l, 64-71 pose-h, 72-79 pose-l; columns 0-31 code, 32-39 pose.
+//   Operand slot (8 KB): MN atom a at a * 4096; inside, K atom q (pixels 8q..8q+7) at q * 1024, pixel row r at r * 128,
+//   16-byte chunk c at (c ^ r) * 16.  Feature slots (2 bytes each):
+//     atom 0:  chunk c = [ code-h 4c..4c+3 | code-m 4c..4c+3 ]   (one 16-byte store per thread and 4 features)
+//     atom 1:  [ pose-h 0-7 | pose-m 8-15 | code-l 16-47 | pose-l 48-55 | zero 56-63 ]
+//   Accumulator rows (TMEM lanes) = slots of atom 0 then atom 1; columns = slots of atom 0 then slots 0-15 of atom 1.
 //   The fp32 accumulator in TMEM adds with truncation (measured: ~ -2^-24 relative per k-step), so a chain is cut every
 //   kFlushTiles tiles.
 //
 // The static tile->CTA assignment, the in-item tile permutation, the per-CTA partials and the wide deterministic
-// finalize are those of the fp32 kernel.  The round-1 kernel (TMA-staged tiles, operand warps transposing into a TMEM
-// A operand) and two intermediate redesigns are kept under tools/experiments/ with their measurements.
+// finalize are those of the fp32 kernel.  Earlier data paths (round 1: TMA-staged tiles + operand warps transposing into
+// a TMEM A operand; the tf32 [h;l] x h version of this kernel) are kept under tools/experiments/ with their measurements.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -58,23 +72,27 @@ namespace {
 
 constexpr int C = 32;
 constexpr int TILE = kTcTilePixels;  // 128
-constexpr int NFE = 12;              // front-end warps
-constexpr int THREADS = 512;         // 12 front-end warps, 3 drain warps, control
+constexpr int NFE = 11;              // front-end warps
+constexpr int THREADS = 512;         // 11 front-end warps, control, 4 drain warps
+constexpr int CTRL_WARP = 11;
 #ifndef DFK_TC_SLOTS
-#define DFK_TC_SLOTS 7
+#define DFK_TC_SLOTS 9
 #endif
 constexpr int NSLOT = DFK_TC_SLOTS;  // operand slots; block j uses slot j % NSLOT
-constexpr uint32_t ATOM_BYTES = 512;              // 32 features x 4 pixels
-constexpr uint32_t MN_STRIDE = 8 * ATOM_BYTES;    // the 8 K atoms of one MN atom are contiguous
-constexpr uint32_t SLOT_BYTES = 3 * MN_STRIDE;    // 12288
-constexpr int NB = 48;           // MMA N (40 used)
-constexpr int MM = 128;          // MMA M (80 used)
+constexpr uint32_t ATOM_BYTES = 1024;             // 64 features x 8 pixels, bf16
+constexpr uint32_t MN_STRIDE = 4 * ATOM_BYTES;    // the 4 K atoms of one MN atom are contiguous
+constexpr uint32_t SLOT_BYTES = 2 * MN_STRIDE;    // 8192
+constexpr int NB = kTcCols;      // MMA N = 80
+constexpr int MM = 128;          // MMA M (120 used)
+#ifndef DFK_TC_LOAD_BATCH
+#define DFK_TC_LOAD_BATCH 2
+#endif
 #ifndef DFK_FLUSH_TILES
 #define DFK_FLUSH_TILES 8
 #endif
 constexpr int kFlushTiles = DFK_FLUSH_TILES;  // TMEM accumulation chain length (tiles)
-constexpr uint32_t TMEM_COLS = 128;
-constexpr uint32_t D_COL = 0;  // [0,48), [48,96): two accumulators
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t D_COL = 0;  // [0,80), [80,160): two accumulators
 
 struct SlotMeta {
   int mask;          // bit g: the 8-pixel group g of the block has a valid pixel
@@ -113,7 +131,6 @@ struct ItemSmem {
 
 struct Smem {
   alignas(1024) unsigned char op[NSLOT][SLOT_BYTES];
-  // >= 4 KB follow the ring: the (ignored) fourth MN atom of an M = 128 operand in the last slot reads into them
   alignas(128) ItemSmem item[NFE];
   alignas(8) uint64_t full[NSLOT];
   // done[w]: the MMAs of the block that used front-end warp w's NEXT slot before it have completed.  One barrier per
@@ -126,7 +143,6 @@ struct Smem {
   alignas(16) ChainRec chain[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(ItemSmem) * NFE >= MN_STRIDE, "the ring's tail pad");
 
 // one warp copies an item description to its private shared-memory copy
 __device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, int lane, int cta)
@@ -171,7 +187,30 @@ __device__ __forceinline__ uint32_t div_magic(uint32_t a, uint32_t b, uint32_t m
   rem = r;
   return q;
 }
-__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+// v0, v1 -> packed bf16 pair (v0 in the low half = lower address), round to nearest
+__device__ __forceinline__ uint32_t pack_bf16(float v0, float v1)
+{
+  const __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+// exact three-way split of two values: h = bf16(v), m = bf16(v - h), l = bf16(v - h - m), each as a packed pair
+__device__ __forceinline__ void split3(float v0, float v1, uint32_t& h, uint32_t& m, uint32_t& l)
+{
+  h = pack_bf16(v0, v1);
+  const float r0 = v0 - bf16_lo(h), r1 = v1 - bf16_hi(h);
+  m = pack_bf16(r0, r1);
+  l = pack_bf16(r0 - bf16_lo(m), r1 - bf16_hi(m));
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ void sts64u(uint32_t addr, uint32_t a, uint32_t b)
+{
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b));
+}
 
 // -DDFK_TC_WATCHDOG: a wait that gives up after ~1 s, says who was waiting for what, and traps (bring-up aid: a
 // protocol error becomes a CUDA error with a message instead of a hung device)
@@ -190,12 +229,6 @@ __device__ __noinline__ void wd_wait(uint64_t* bar, uint32_t parity, int what, i
 #define TC_WAIT(bar, parity, what, idx) mbar_wait(bar, parity)
 #endif
 
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d)
-{
-  // no "memory" clobber: the front-end's only plain shared-memory accesses are reads of its item copy and the slot
-  // meta (written after the proxy fence, which does carry the clobber); volatile keeps the stores ordered with the fence
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
-}
 
 // 16 bytes of a code-Jacobian row; rows of items without the BULK flag are only 4-byte aligned
 __device__ __forceinline__ float4 load_chunk(const float* __restrict__ p, bool aligned16)
@@ -229,14 +262,14 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
     for (int w = 0; w < NFE; ++w) mbar_init(&sm.done[w], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm.d_full[b], 2);   // the tcgen05.commit of the chain's MMAs + the control thread's release of the record
-      mbar_init(&sm.d_empty[b], 3);
+      mbar_init(&sm.d_empty[b], 4);
     }
     mbar_fence_init();
   }
-  // the never-written parts of the ring (pose atom chunks 2, 3) must hold zeros
+  // the never-written part of the ring (feature slots 56-63 of atom 1) must hold zeros
   for (int e = tid; e < (int)(NSLOT * SLOT_BYTES / 16); e += THREADS)
     reinterpret_cast<float4*>(&sm.op[0][0])[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (warp == 15) {
+  if (warp == CTRL_WARP) {
     tmem_alloc(&sm.tmem_base, TMEM_COLS);
     tmem_relinquish();
   }
@@ -247,7 +280,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
   const uint32_t tbase = sm.tmem_base;
 
   // register budget per role (warpgroup granularity): 12 x 32 x 72 + 4 x 32 x 40 = 32768 = half the register file
-  if (warp < NFE) {
+  if (warp <= CTRL_WARP) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -257,22 +290,19 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
     if (warp < NFE) {
       // ======================================================================= front-end warps
       ItemSmem& I = sm.item[warp];
-      int it = 0;
-      int cur_item = -1;
-      uint32_t item_lo = 0, item_hi = 0;  // global tile range of the item in shared memory
+      int it = -1;  // the item in shared memory
       uint32_t done_phase = 0;
       for (int j = warp; j < nblocks; j += NFE) {
         const int i = j >> 2, b = j & 3;
         const int g = g_lo + i;
-        if (cur_item < 0 || (uint32_t)g >= item_hi) {
+        if (it < 0 || (uint32_t)g >= I.tile_begin + I.num_tiles) {
+          if (it < 0) it = 0;
           while ((uint32_t)g >= items[it].tile_begin + items[it].num_tiles) ++it;
           __syncwarp();
           load_item(I, items[it], lane, cta);
           __syncwarp();
-          cur_item = it;
-          item_lo = I.tile_begin;
-          item_hi = I.tile_begin + I.num_tiles;
         }
+        const uint32_t item_lo = I.tile_begin;
         // the tile sequence enters a new item with this block
         const bool seq_changed = (b == 0) && ((i == 0) || ((uint32_t)(g - 1) < item_lo));
         const uint32_t k = (uint32_t)g - item_lo;
@@ -295,13 +325,12 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           pxx -= W;
           ++py;
         }
-        const float* __restrict__ jac = I.jac;
         const uint32_t joff = py * I.jac_pitch + pxx * C;  // this pixel's code-Jacobian row (floats)
         float feat[8];
         bool ok = false;
         if (blk_live) {
 #ifndef DFK_TC_NOPREFETCH
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(jac + joff));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(I.jac + joff));
 #endif
           const float xn = __ldg(I.ray_tab + pxx);
           const float yn = __ldg(I.ray_tab + W + py);
@@ -316,7 +345,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
 #pragma unroll
             for (int i8 = 0; i8 < 8; ++i8) {
               const uint32_t offk = __shfl_sync(0xffffffffu, joff, 4 * i8 + (lane >> 3));
-              float p = chunk_dot(load_chunk(jac + offk + 4 * (lane & 7), a16), cc);
+              float p = chunk_dot(load_chunk(I.jac + offk + 4 * (lane & 7), a16), cc);
               p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 4));
               p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 2));
               p = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 1));
@@ -358,8 +387,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         }
         const unsigned bal = __ballot_sync(0xffffffffu, ok);
         const int nvb = __popc(bal);
-        const int mask = ((bal & 0xffu) ? 1 : 0) | ((bal & 0xff00u) ? 2 : 0) | ((bal & 0xff0000u) ? 4 : 0) |
-                         ((bal & 0xff000000u) ? 8 : 0);
+        const int mask = ((bal & 0xffffu) ? 1 : 0) | ((bal & 0xffff0000u) ? 2 : 0);  // non-empty 16-pixel groups
         // ---- the operand slot: free once the MMAs of block j - NSLOT have completed (the control thread commits them
         // to this warp's barrier; one commit per block of this warp, in order) ------------------------------------------
         const int slot = j % NSLOT;
@@ -369,52 +397,60 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         }
         if (nvb > 0) {
           const uint32_t sbase = smem_u32(&sm.op[slot][0]);
-          // code atoms: iteration i8 covers the K atom of pixels 4 i8 .. 4 i8 + 3; this lane holds the 16-byte chunk
-          // lane & 7 of pixel 4 i8 + lane / 8 -> 512 contiguous bytes per warp load
-          const int r = lane >> 3;
-          const uint32_t dst0 = sbase + (uint32_t)r * 128u + (uint32_t)(((((lane & 7) >> 1) ^ r) << 5) | ((lane & 1) << 4));
-          float4 v[8];
+          // code features: iteration i8 covers pixels 4 i8 .. 4 i8 + 3; 8 lanes hold the eight 16-byte chunks of one
+          // pixel's row (512 contiguous bytes per warp load).  Lane groups 0-7 / 8-15 / 16-23 / 24-31 take pixels
+          // 0 / 2 / 1 / 3, so that the two rows one half-warp stores 8 bytes per lane to (code-l) sit in different banks
+          const int r = ((lane >> 3) & 1) * 2 + (lane >> 4);
+          const int c = lane & 7;
+          // one 16-pixel group (= one k-step of the MMA) at a time, its four row loads in two batches of two (registers)
 #pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const int kp = 4 * i8 + r;
-            const uint32_t offk = __shfl_sync(0xffffffffu, joff, kp);
-            v[i8] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int gq = 0; gq < 2; ++gq) {
+            if (!((mask >> gq) & 1)) continue;  // no valid pixel in the group: no loads, no stores, no MMA
+#pragma unroll
+            for (int ub = 0; ub < 4; ub += DFK_TC_LOAD_BATCH) {
+              float4 v[DFK_TC_LOAD_BATCH];
+#pragma unroll
+              for (int u = 0; u < DFK_TC_LOAD_BATCH; ++u) {
+                const int kp = 16 * gq + 4 * (ub + u) + r;
+                const uint32_t offk = __shfl_sync(0xffffffffu, joff, kp);
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #ifdef DFK_EXP_NOJC  // experiment (wrong results): no code-Jacobian traffic
-            if ((bal >> kp) & 1u) v[i8] = make_float4(0.1f * (float)offk, 0.2f, 0.3f, 0.4f);
+                if ((bal >> kp) & 1u) v[u] = make_float4(0.1f * (float)offk, 0.2f, 0.3f, 0.4f);
 #else
-            if ((bal >> kp) & 1u) v[i8] = load_chunk(jac + offk + 4 * (lane & 7), a16);
+                if ((bal >> kp) & 1u) v[u] = load_chunk(I.jac + offk + 4 * c, a16);
 #endif
-          }
+              }
 #pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const float sk = __shfl_sync(0xffffffffu, feat[0], 4 * i8 + r);
-            if ((mask >> (i8 >> 1)) & 1) {
-              const float h0 = sk * v[i8].x, h1 = sk * v[i8].y, h2 = sk * v[i8].z, h3 = sk * v[i8].w;
-              const uint32_t dst = dst0 + (uint32_t)i8 * ATOM_BYTES;
-#ifdef DFK_EXP_NOSTORE  // experiment (wrong results): one store instead of two
-              sts128(dst, h0 + tf32_trunc(h1), h1, h2 - tf32_trunc(h3), h3);
-#else
-              sts128(dst, h0, h1, h2, h3);  // the tensor core truncates: h rows carry the raw values
-              sts128(dst + MN_STRIDE, h0 - tf32_trunc(h0), h1 - tf32_trunc(h1), h2 - tf32_trunc(h2), h3 - tf32_trunc(h3));
-#endif
+              for (int u = 0; u < DFK_TC_LOAD_BATCH; ++u) {
+                const int i8 = 4 * gq + ub + u;
+                const float sk = __shfl_sync(0xffffffffu, feat[0], 4 * i8 + r);
+                const int rr = 4 * (i8 & 1) + r;  // pixel row inside its K atom (i8 >> 1)
+                const uint32_t row = sbase + (uint32_t)(i8 >> 1) * ATOM_BYTES + (uint32_t)rr * 128u;
+                uint32_t h0, m0, l0, h1, m1, l1;
+                split3(sk * v[u].x, sk * v[u].y, h0, m0, l0);
+                split3(sk * v[u].z, sk * v[u].w, h1, m1, l1);
+                sts128u(row + (uint32_t)((c ^ rr) << 4), h0, h1, m0, m1);  // atom 0, chunk c: h 4c..4c+3 | m 4c..4c+3
+                // atom 1, code-l slots 16 + 4c ..: byte 32 + 8c of the row = chunk 2 + c/2, half c & 1
+                sts64u(row + MN_STRIDE + (uint32_t)((((2 + (c >> 1)) ^ rr) << 4) | ((c & 1) << 3)), l0, l1);
+              }
             }
           }
-          // pose atom: this thread's pixel = K position `lane`: h of the 7 pose / residual values in chunk 0, l in chunk 1.
-          // Lanes of odd K atoms write the two 16-byte halves of a chunk in the opposite order: the 8 lanes of a
-          // quarter warp (two K atoms x four rows) then hit 8 different bank groups
+          // pose / residual features: this thread's pixel = K position `lane`: chunks 0 (h), 1 (m), 6 (l) of its atom-1 row;
+          // one term at a time (the residuals replace the values in place) keeps the register footprint small
           {
-            const int rp = lane & 3;
-            const bool odd = (lane & 4) != 0;
-            const uint32_t row = sbase + 2u * MN_STRIDE + (uint32_t)(lane >> 2) * ATOM_BYTES + (uint32_t)rp * 128u;
-            const uint32_t ch = row + ((uint32_t)rp << 5) + (odd ? 16u : 0u);         // chunk 0 ^ rp
-            const uint32_t cl = row + ((uint32_t)(rp ^ 1) << 5) + (odd ? 16u : 0u);   // chunk 1 ^ rp
-            const float a0 = feat[1], a1 = feat[2], a2 = feat[3], a3 = feat[4], b0 = feat[5], b1 = feat[6], b2 = feat[7];
-            const float la0 = a0 - tf32_trunc(a0), la1 = a1 - tf32_trunc(a1), la2 = a2 - tf32_trunc(a2), la3 = a3 - tf32_trunc(a3);
-            const float lb0 = b0 - tf32_trunc(b0), lb1 = b1 - tf32_trunc(b1), lb2 = b2 - tf32_trunc(b2);
-            sts128(ch, odd ? b0 : a0, odd ? b1 : a1, odd ? b2 : a2, odd ? 0.0f : a3);
-            sts128(ch ^ 16u, odd ? a0 : b0, odd ? a1 : b1, odd ? a2 : b2, odd ? a3 : 0.0f);
-            sts128(cl, odd ? lb0 : la0, odd ? lb1 : la1, odd ? lb2 : la2, odd ? 0.0f : la3);
-            sts128(cl ^ 16u, odd ? la0 : lb0, odd ? la1 : lb1, odd ? la2 : lb2, odd ? la3 : 0.0f);
+            const int rr = lane & 7;
+            const uint32_t row = sbase + MN_STRIDE + (uint32_t)(lane >> 3) * ATOM_BYTES + (uint32_t)rr * 128u;
+            float f0 = feat[1], f1 = feat[2], f2 = feat[3], f3 = feat[4], f4 = feat[5], f5 = feat[6], f6 = feat[7];
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              const uint32_t p0 = pack_bf16(f0, f1), p1 = pack_bf16(f2, f3), p2 = pack_bf16(f4, f5), p3 = pack_bf16(f6, 0.0f);
+              const int chunk = term == 0 ? 0 : (term == 1 ? 1 : 6);
+              sts128u(row + (uint32_t)((chunk ^ rr) << 4), p0, p1, p2, p3);
+              if (term < 2) {
+                f0 -= bf16_lo(p0); f1 -= bf16_hi(p0); f2 -= bf16_lo(p1); f3 -= bf16_hi(p1);
+                f4 -= bf16_lo(p2); f5 -= bf16_hi(p2); f6 -= bf16_lo(p3);
+              }
+            }
           }
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the MMA's operand fetch
         }
@@ -427,7 +463,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.full[slot]);
       }
-    } else if (warp == 15) {
+    } else if (warp == CTRL_WARP) {
       // ======================================================================= control warp
       // The whole warp walks the blocks (uniform control flow: waits, meta, chain bookkeeping are done redundantly by all
       // lanes, which keeps the loop free of divergence); one elected lane issues the MMAs, the commits and the records.
@@ -436,11 +472,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
       {
         const bool leader = elect_one_sync();
 #ifdef DFK_EXP_SMALLMMA  // experiment (wrong results): same issue pattern, a fraction of the operand fetch
-        const uint32_t idesc = make_idesc_tf32(64, 16) | kIdescAMnMajor | kIdescBMnMajor;
+        const uint32_t idesc = make_idesc_bf16(64, 16) | kIdescAMnMajor | kIdescBMnMajor;
 #else
-        const uint32_t idesc = make_idesc_tf32(MM, NB) | kIdescAMnMajor | kIdescBMnMajor;
+        const uint32_t idesc = make_idesc_bf16(MM, NB) | kIdescAMnMajor | kIdescBMnMajor;
 #endif
-        const uint32_t desc_hi = (ATOM_BYTES >> 4) | (1u << 14) | (1u << 29);  // SBO | version 1 | SWIZZLE_128B_BASE32B
+        const uint32_t desc_hi = (ATOM_BYTES >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
         const uint32_t ring_lo = (smem_u32(&sm.op[0][0]) & 0x3ffffu) >> 4;
         int e = -1, tiles_in_chain = 0;
         uint32_t first = 1;
@@ -493,24 +529,21 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
           if (leader) {
             const uint32_t d_addr = tbase + D_COL + NB * (uint32_t)(e & 1);
             const uint32_t lo = ring_lo + (uint32_t)slot * (SLOT_BYTES >> 4);
-#ifdef DFK_EXP_NOMMA
-            if (meta.x == 15) {
+            const uint32_t dlo = lo | ((MN_STRIDE >> 4) << 16);  // A and B: same start, same LBO; B is the first 80 rows
+#ifdef DFK_EXP_NOMMA  // experiment (wrong results): no tensor-core work, no operand fetch
+            if (meta.x == 3) {
               first = 0;
             } else
 #endif
-            if (meta.x == 15) {  // the common case: four k-steps back to back
-              umma_tf32_ss_x4(d_addr, lo | ((MN_STRIDE >> 4) << 16), lo | ((2 * MN_STRIDE >> 4) << 16), desc_hi, idesc, first ^ 1u,
-                              (2 * ATOM_BYTES) >> 4);
+            if (meta.x == 3) {  // the common case: two k-steps back to back
+              umma_bf16_ss_x2(d_addr, dlo, desc_hi, idesc, first ^ 1u, (2 * ATOM_BYTES) >> 4);
               first = 0;
             } else {
 #pragma unroll
-              for (int gq = 0; gq < 4; ++gq) {
+              for (int gq = 0; gq < 2; ++gq) {
                 if ((meta.x >> gq) & 1) {
-                  const uint32_t adv = (uint32_t)gq * ((2 * ATOM_BYTES) >> 4);  // two K atoms per k-step
-#ifndef DFK_EXP_NOMMA  // experiment (wrong results): no tensor-core work, no operand fetch
-                  umma_tf32_ss(d_addr, ((uint64_t)desc_hi << 32) | (lo + adv) | ((MN_STRIDE >> 4) << 16),
-                               ((uint64_t)desc_hi << 32) | (lo + adv) | ((2 * MN_STRIDE >> 4) << 16), idesc, first == 0);
-#endif
+                  const uint64_t d = ((uint64_t)desc_hi << 32) | (dlo + (uint32_t)gq * ((2 * ATOM_BYTES) >> 4));  // two K atoms per k-step
+                  umma_bf16_ss(d_addr, d, d, idesc, first == 0);
                   first = 0;
                 }
               }
@@ -528,8 +561,8 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         close_chain(true, true);
       }
     } else {
-      // ======================================================================= drain warps (TMEM lanes 0..95)
-      const int ow = warp & 3;  // 0, 1, 2 = the lane quarter this warp may access
+      // ======================================================================= drain warps (TMEM lanes 0..127)
+      const int ow = warp & 3;  // the lane quarter this warp may access
       const uint32_t lane_taddr = tbase + ((uint32_t)(ow * 32) << 16);
       const int row = ow * 32 + lane;  // TMEM lane == row of the partial
       for (int e = 0;; ++e) {
@@ -538,13 +571,16 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
         tc_fence_after();
         const ChainRec rec = sm.chain[b];
         float* P = partials + (size_t)rec.pslot * kTcPartialFloats;
-        // three passes of 16 accumulator columns keep the register footprint small.  The first chain of an item in
+        // five passes of 16 accumulator columns keep the register footprint small.  The first chain of an item in
         // this CTA stores, later chains add with fire-and-forget red.global.add.f32: this thread is the only writer
         // of its row and issues its updates in program order, so the sum order is fixed.
+#ifdef DFK_EXP_NODRAIN  // experiment (wrong results): chains are not moved to global memory
+        if (false) {
+#else
         if (rec.valid > 0 || rec.fresh) {
+#endif
 #pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const int ncol = pass < 2 ? 16 : kTcCols - 32;  // columns 40..47 are padding
+          for (int pass = 0; pass < kTcCols / 16; ++pass) {
             uint32_t v[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) v[c] = 0u;
@@ -558,12 +594,11 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
             if (rec.fresh) {
 #pragma unroll
               for (int c = 0; c < 16; ++c)
-                if (c < ncol) __stcg(dcol + c * kTcRowsPad, __uint_as_float(v[c]));
+                __stcg(dcol + c * kTcRowsPad, __uint_as_float(v[c]));
             } else {
 #pragma unroll
               for (int c = 0; c < 16; ++c)
-                if (c < ncol)
-                  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dcol + c * kTcRowsPad), "f"(__uint_as_float(v[c])) : "memory");
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dcol + c * kTcRowsPad), "f"(__uint_as_float(v[c])) : "memory");
             }
           }
         }
@@ -578,7 +613,7 @@ sfm_step_tc_kernel(const SfmItemDev* __restrict__ items, int num_items, int num_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 15) tmem_dealloc(tbase, TMEM_COLS);
+  if (warp == CTRL_WARP) tmem_dealloc(tbase, TMEM_COLS);
 }
 
 }  // namespace

@@ -15,7 +15,9 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_subpipe_tmem_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct",
-        "l1tex__t_sector_hit_rate.pct", "l1tex__t_bytes.sum", "lts__t_bytes.sum"]
+        "l1tex__t_sector_hit_rate.pct", "l1tex__t_bytes.sum", "lts__t_bytes.sum",
+        "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg"]
 for r in rows[2:]:
     d = dict(zip(hdr, r))
     print("==", d.get("Kernel Name", "?")[:90], "block", d.get("Block Size"), "grid", d.get("Grid Size"))

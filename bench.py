@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--identity-pose", action="store_true", help="100%% inliers (worst-case work) instead of the ~60%% of the reference test poses")
     ap.add_argument("--no-verify", action="store_true",
                     help="skip the parity check of the TIMED batch against the CPU oracle (outside the timed region)")
+    ap.add_argument("--reserve-sms", type=int, default=-1,
+                    help="SMs the persistent step kernel leaves free for the concurrent all-reduce of the previous step "
+                         "(dfk_set_sm_limit); default: 4 when the job has more than one rank, else 0")
     ap.add_argument("--sustain-seconds", type=float, default=1.2,
                     help="after the K timed steps, repeat the same step back to back for about this long (clocks are sampled "
                          "over both regions); reported as `sustained`")
@@ -454,6 +457,9 @@ def main():
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # the per-step collective is a few hundred KB: two channels are plenty, and a small NCCL grid fits into the SMs the step
+        # kernel leaves free (see --reserve-sms)
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
     cfg = CONFIGS[args.config]
@@ -493,6 +499,9 @@ def main():
         return np.ascontiguousarray(jac), img0
 
     al = SfmAligner(cs, gram_mode=args.gram)
+    reserve_sms = args.reserve_sms if args.reserve_sms >= 0 else (4 if world > 1 else 0)
+    if reserve_sms > 0:
+        al.SetSmLimit(torch.cuda.get_device_properties(dev).multi_processor_count - reserve_sms)
     items, item_pair, item_sizes, item_src = [], [], [], []   # item_src: (variation of img0/jac side, level) for --verify
     if cfg["kind"] == "pairs":
         P = cfg["pairs_per_gpu"]            # pairs of THIS rank; the window of all ranks has world * P pairs
@@ -573,13 +582,31 @@ def main():
     read_profile()
     _lib.check(al.handle, lib.dfk_set_profiling(al.handle, 1))
 
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    def aligned_start():
+        """barrier + synchronize (the contract), then one tiny all-reduce ON the launch stream right before the start event:
+        the host-side barrier releases the ranks up to a millisecond apart (8 Python processes), and a rank that starts
+        early would wait that skew out inside its first collective and count it; the in-stream collective completes on all
+        ranks within microseconds, so every rank's clock starts at the same point of the job"""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.all_reduce(align_buf)
+    align_buf = torch.zeros(1, device=dev)
+
+    aligned_start()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Lead-in: the W warm-up steps are issued again BEHIND the barrier + synchronize and run straight into the timed steps
+    # (the start event is recorded in-stream between them).  Each step overlaps the previous step's collective and the
+    # host runs ahead of the device; coming out of a synchronize that pipeline takes a few steps to fill (0.5 - 4 ms at
+    # N = 2 .. 8), which a 20-step region would charge to the steady-state rate the metric is about.  The K timed steps,
+    # their collectives and the final drain are all inside [e0, e1].
+    lead_in = max(3, args.warmup)
+    for _ in range(lead_in):
+        step()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -592,7 +619,9 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    kern_ms, kern_n, launches = read_profile()
+    kern_ms, kern_n, launches = read_profile()   # covers the lead-in steps too: scale the counts to the K timed steps
+    launches = launches * args.steps / (lead_in + args.steps)
+    kern_ms, kern_n = kern_ms * args.steps / (lead_in + args.steps), kern_n * args.steps / (lead_in + args.steps)
     pairs_all_ranks = torch.tensor([float(P)], device=dev)
     if world > 1:
         dist.all_reduce(pairs_all_ranks)
@@ -604,9 +633,7 @@ def main():
     sustained = None
     if args.sustain_seconds > 0:
         n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(total_ms / args.steps, 1e-3)) + 1)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        aligned_start()
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         q0.record()
         for _ in range(n_sus):
@@ -745,10 +772,15 @@ def main():
                        "parallelism": f"pairs sharded over {n_gpus} GPU(s); every step assembles the window's block-sparse "
                                       "normal equations on the device" + (
                            "; ONE NCCL all-reduce of that buffer per step, asynchronous, overlapped with the next step's "
-                           "launch" if world > 1 else "")},
+                           f"launch; the step kernel's grid leaves {reserve_sms} SMs to that collective (dfk_set_sm_limit)"
+                           if world > 1 else ""),
+                       "reserved_sms": reserve_sms,
+                       "timing": f"barrier + synchronize, {lead_in} untimed lead-in steps, start event in-stream, EXACTLY "
+                                 f"{args.steps} timed steps + the drain of their collectives, stop event, synchronize + "
+                                 "barrier; max over ranks of the per-rank event time"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "sfm_step kernel (per-tile warp + Gram)", "launches_timed": kern_n,
+                         "kernel": "sfm_step kernel (per-tile warp + Gram)", "launches_timed": int(round(kern_n)),
                          "avg_launch_ms": kern_avg_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_launch},
             "cpu_baseline": cpu,
@@ -756,7 +788,7 @@ def main():
             "single_launch": single,
             "sustained": sustained,
             "parity": parity,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(round(launches)),
             "clocks": clocks,
         }
         print(json.dumps(out))

@@ -76,6 +76,7 @@ SYMBOLS = {
     "dfk_create": (C.c_int, [C.c_int, C.POINTER(_H)]),
     "dfk_destroy": (C.c_int, [_H]),
     "dfk_set_stream": (C.c_int, [_H, C.c_void_p]),
+    "dfk_set_sm_limit": (C.c_int, [_H, C.c_int]),
     "dfk_use_own_stream": (C.c_int, [_H]),
     "dfk_get_stream": (C.c_void_p, [_H]),
     "dfk_synchronize": (C.c_int, [_H]),

@@ -170,6 +170,11 @@ class SfmAligner:
     def handle(self):
         return self._hd.h
 
+    def SetSmLimit(self, num_sms: int):
+        """size the persistent RunStep grids for `num_sms` SMs (0 = all): leaves room for a kernel on another stream, e.g.
+        the window's all-reduce of the previous step (dfk_set_sm_limit)"""
+        check(self._hd.h, lib().dfk_set_sm_limit(self._hd.h, int(num_sms)))
+
     def SetGramMode(self, mode: str):
         m = {"auto": _lib.DFK_GRAM_AUTO, "fp32": _lib.DFK_GRAM_FP32, "tf32x3": _lib.DFK_GRAM_TF32X3}[mode]
         check(self._hd.h, lib().dfk_sfm_set_gram_mode(self._hd.h, m))

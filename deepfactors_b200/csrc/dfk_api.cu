@@ -21,6 +21,7 @@ using namespace dfk;
 struct DfkContext {
   int device = 0;
   int num_sms = 1;
+  int sm_limit = 0;  // dfk_set_sm_limit: SMs the persistent step kernels may occupy (0 = all)
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -473,7 +474,8 @@ DfkStatus run_batch(DfkHandle h, const DfkSfmWorkItem* items, int n, int code_si
     h->codes_host.assign((size_t)n * code_size, 0.0f);
   }
   const int ctas_per_sm = tc ? 2 : (wide ? 1 : sfm_fp32_ctas_per_sm(code_size));
-  DfkStatus st = build_items(h, items, n, code_size, tile_px, ctas_per_sm * h->num_sms,
+  const int sms = (h->sm_limit > 0 && h->sm_limit < h->num_sms) ? h->sm_limit : h->num_sms;
+  DfkStatus st = build_items(h, items, n, code_size, tile_px, ctas_per_sm * sms,
                              tc, h->codes_dev, &plan);
   if (st != DFK_OK) return st;
   if (any_fused)
@@ -614,6 +616,20 @@ DfkStatus dfk_use_own_stream(DfkHandle h)
     return DFK_OK;
   } catch (...) {  // std::bad_alloc / std::length_error from host containers must not cross the C ABI
     return oom(h);
+  }
+}
+
+DfkStatus dfk_set_sm_limit(DfkHandle h, int num_sms)
+{
+  if (!h) return DFK_ERR_INVALID_ARG;
+  try {
+    if (num_sms < 0) return fail(h, DFK_ERR_INVALID_ARG, "[dfk_set_sm_limit] num_sms < 0");
+    h->sm_limit = num_sms;
+    return DFK_OK;
+  } catch (const std::bad_alloc&) {
+    return oom(h);
+  } catch (...) {
+    return DFK_ERR_CUDA;
   }
 }
 

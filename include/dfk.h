@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define DFK_VERSION 102
+#define DFK_VERSION 103
 
 typedef enum {
   DFK_OK = 0,
@@ -107,6 +107,13 @@ DfkStatus dfk_destroy(DfkHandle h);
  * private non-blocking stream; dfk_use_own_stream returns to it. */
 DfkStatus dfk_set_stream(DfkHandle h, void* cuda_stream);
 DfkStatus dfk_use_own_stream(DfkHandle h);
+/* The RunStep kernels are persistent: one launch fills every SM for its whole duration, so a kernel that arrives on
+ * another stream meanwhile (the collective of the previous step on a multi-GPU window, bench.py) finds no room, starts
+ * when the first CTAs retire and then holds SMs the NEXT step's grid was sized for.  num_sms > 0 sizes the grids for
+ * that many SMs and leaves the rest to the concurrent kernel; 0 = all SMs (default).  Results do not depend on it
+ * beyond the summation order of the per-CTA partials (deterministic for a given limit).  No reference counterpart: the
+ * reference synchronises the device after every launch (launch_utils.h:28). */
+DfkStatus dfk_set_sm_limit(DfkHandle h, int num_sms);
 void* dfk_get_stream(DfkHandle h);
 DfkStatus dfk_synchronize(DfkHandle h);
 const char* dfk_last_error(DfkHandle h);

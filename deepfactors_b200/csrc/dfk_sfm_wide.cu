@@ -23,6 +23,7 @@
 #include "dfk_async.cuh"
 #include "dfk_geom.cuh"
 #include "dfk_internal.h"
+#include "dfk_tile_stage.cuh"
 
 namespace dfk {
 
@@ -50,23 +51,7 @@ struct TileMeta {
   int pad;
 };
 
-struct ItemSmem {
-  float q[4];
-  float t[3];
-  float R[9];
-  float fx, fy, u0, v0, border, ulim, vlim, min_dpt, avg_dpt, huber_delta;
-  const float* img0;
-  const float* img1;
-  const float* dpt0;
-  float* valid0;
-  const float* jac;
-  const float* grad1;
-  uint32_t img0_pitch, img1_pitch, dpt0_pitch, valid0_pitch, jac_pitch, grad1_pitch;
-  uint32_t width, height, num_pixels, tile_begin, num_tiles, perm_mul, flags, slot;
-  float* dpt_out;  // fused depth decode (ITEM_FLAG_FUSED_DEPTH): decoded depth goes here, dpt0 stages prx_orig
-  uint32_t dpt_out_pitch;
-  alignas(16) float code[kMaxCode];
-};
+using ItemSmem = StagedItem<kMaxCode>;  // dfk_tile_stage.cuh
 
 template <int C>
 struct Smem {
@@ -82,82 +67,6 @@ struct Smem {
   ItemSmem item;
   int cnt[W::FE_WARPS];
 };
-
-__device__ __forceinline__ void load_item(ItemSmem& dst, const SfmItemDev& src, int tid, int cta)
-{
-  if (tid < 4) dst.q[tid] = src.q[tid];
-  if (tid < 3) dst.t[tid] = src.t[tid];
-  if (tid < 9) dst.R[tid] = src.R[tid];
-  if (tid == 32) {
-    dst.fx = src.fx; dst.fy = src.fy; dst.u0 = src.u0; dst.v0 = src.v0;
-    dst.border = src.border; dst.ulim = src.ulim; dst.vlim = src.vlim;
-    dst.min_dpt = src.min_dpt; dst.avg_dpt = src.avg_dpt; dst.huber_delta = src.huber_delta;
-    dst.img0 = src.img0; dst.img1 = src.img1; dst.dpt0 = src.dpt0; dst.valid0 = src.valid0;
-    dst.jac = src.jac; dst.grad1 = src.grad1;
-  }
-  if (tid == 33) {
-    dst.img0_pitch = src.img0_pitch; dst.img1_pitch = src.img1_pitch; dst.dpt0_pitch = src.dpt0_pitch;
-    dst.valid0_pitch = src.valid0_pitch; dst.jac_pitch = src.jac_pitch; dst.grad1_pitch = src.grad1_pitch;
-    dst.width = src.width; dst.height = src.height; dst.num_pixels = src.num_pixels;
-    dst.tile_begin = src.tile_begin; dst.num_tiles = src.num_tiles; dst.perm_mul = src.perm_mul;
-    dst.flags = src.flags;
-    dst.slot = src.partial_begin + (uint32_t)cta - src.first_cta;
-    dst.dpt_out = src.dpt_out; dst.dpt_out_pitch = src.dpt_out_pitch;
-  }
-}
-
-// fused depth decode: the item's latent code -> shared memory (callers sync afterwards)
-__device__ __forceinline__ void load_code(ItemSmem& dst, const SfmItemDev& src, int code_size, int tid, int nthreads)
-{
-  if (src.flags & ITEM_FLAG_FUSED_DEPTH)
-    for (int k = tid; k < code_size; k += nthreads) dst.code[k] = __ldg(src.code + k);
-}
-
-template <int C>
-__device__ __forceinline__ void issue_tile_loads(Smem<C>& sm, const SfmItemDev* __restrict__ items, int it, int g,
-                                                 int st)
-{
-  constexpr int TILE = WideCfg<C>::TILE;
-  const SfmItemDev& I = items[it];
-  const uint32_t k = (uint32_t)g - I.tile_begin;
-  const uint32_t tau = (uint32_t)(((uint64_t)k * I.perm_mul) % I.num_tiles);
-  const uint32_t p0 = tau * TILE;
-  const uint32_t n = min((uint32_t)TILE, I.num_pixels - p0);
-  const uint32_t W = I.width;
-  uint32_t y = p0 / W;
-  uint32_t x = p0 - y * W;
-  mbar_arrive_expect_tx(&sm.full_tma[st], n * (C + 2) * 4u);
-  uint32_t slot = 0;
-  while (slot < n) {
-    const uint32_t seg = min(W - x, n - slot);
-    bulk_g2s(&sm.jc[st][slot * C], I.jac + (size_t)y * I.jac_pitch + (size_t)x * C, seg * C * 4u, &sm.full_tma[st]);
-    bulk_g2s(&sm.img0[st][slot], I.img0 + (size_t)y * I.img0_pitch + x, seg * 4u, &sm.full_tma[st]);
-    bulk_g2s(&sm.dpt0[st][slot], I.dpt0 + (size_t)y * I.dpt0_pitch + x, seg * 4u, &sm.full_tma[st]);
-    slot += seg;
-    x = 0;
-    ++y;
-  }
-}
-
-template <int C>
-__device__ __forceinline__ void coop_tile_loads(Smem<C>& sm, const ItemSmem& I, uint32_t p0, uint32_t n, int st,
-                                                int tid)
-{
-  constexpr int FE = WideCfg<C>::FE_THREADS;
-  const uint32_t W = I.width;
-  for (uint32_t s = tid; s < n; s += FE) {
-    const uint32_t p = p0 + s;
-    const uint32_t y = p / W, x = p - y * W;
-    sm.img0[st][s] = __ldg(I.img0 + (size_t)y * I.img0_pitch + x);
-    sm.dpt0[st][s] = __ldg(I.dpt0 + (size_t)y * I.dpt0_pitch + x);
-  }
-  for (uint32_t e = tid; e < n * C; e += FE) {
-    const uint32_t s = e / C, kk = e - s * C;
-    const uint32_t p = p0 + s;
-    const uint32_t y = p / W, x = p - y * W;
-    sm.jc[st][e] = __ldg(I.jac + (size_t)y * I.jac_pitch + (size_t)x * C + kk);
-  }
-}
 
 template <int C>
 __global__ void __launch_bounds__(WideCfg<C>::THREADS, 1)
@@ -206,7 +115,7 @@ sfm_step_wide_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
       for (int j = 0; j < kStages && g_lo + j < g_hi; ++j) {
         const int g = g_lo + j;
         while ((uint32_t)g >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
-        if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads<C>(sm, items, it_pf, g, j);
+        if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads<C, WideCfg<C>::TILE>(sm, items, it_pf, g, j);
       }
     }
 
@@ -217,7 +126,7 @@ sfm_step_wide_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
       const bool changed = (it != cur_item);
       if (changed) {
         named_bar_sync(1, FE);
-        load_item(sm.item, items[it], tid, cta);
+        load_item(sm.item, items[it], tid, W::FE_THREADS, cta);
         load_code(sm.item, items[it], C, tid, FE);
         cur_item = it;
         named_bar_sync(1, FE);
@@ -231,7 +140,7 @@ sfm_step_wide_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
         mbar_wait(&sm.full_tma[st], (tma_phase_bits >> st) & 1u);
         tma_phase_bits ^= (1u << st);
       } else {
-        coop_tile_loads<C>(sm, I, p0, n, st, tid);
+        coop_tile_loads<C, WideCfg<C>::FE_THREADS>(sm, I, p0, n, st, tid);
         named_bar_sync(1, FE);
       }
 
@@ -315,7 +224,7 @@ sfm_step_wide_kernel(const SfmItemDev* __restrict__ items, int num_items, int nu
         const int gn = g + kStages;
         if (gn < g_hi) {
           while ((uint32_t)gn >= items[it_pf].tile_begin + items[it_pf].num_tiles) ++it_pf;
-          if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads<C>(sm, items, it_pf, gn, st);
+          if (items[it_pf].flags & ITEM_FLAG_BULK) issue_tile_loads<C, WideCfg<C>::TILE>(sm, items, it_pf, gn, st);
         }
       }
     }

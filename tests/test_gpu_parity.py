@@ -218,6 +218,38 @@ def test_sfm_batch_matches_single_calls_and_is_deterministic(torch_mod, mode):
         assert abs(got.residual - ref.residual) <= 1e-5 * max(ref.residual, 1e-12)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_sfm_sm_limit_changes_the_grid_not_the_result(torch_mod, mode):
+    """dfk_set_sm_limit (SMs left to a concurrent collective): same inliers, same sums up to the summation grouping,
+    bitwise reproducible for a given limit, and 0 restores the full grid"""
+    torch = torch_mod
+    from deepfactors_b200.aligners import SfmAligner
+    al = SfmAligner(32, gram_mode=mode)
+    pair = synth.make_pair(640, 480, 32, 3, seed=31, code_sigma=0.3)
+    items = []
+    for L in pair.levels:
+        dev = upload_level(torch, L)
+        items.append(dict(pose0=pair.pose0, pose1=pair.pose1, cam=L.cam, **{k: dev[k] for k in (
+            "img0", "img1", "dpt0", "valid0", "prx0_jac", "grad1")}))
+    work = al.make_work_items(items)
+    full = al.RunStepBatch(work).clone()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for limit in (sms - 4, 7, 1):
+        al.SetSmLimit(limit)
+        a = al.RunStepBatch(work).clone()
+        b = al.RunStepBatch(work).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(a, b), f"limit {limit}: not bitwise reproducible"
+        for got, ref in zip(al.unpack(a), al.unpack(full)):
+            assert got.inliers == ref.inliers
+            assert np.abs(got.JtJ - ref.JtJ).max() <= 1e-5 * np.abs(ref.JtJ).max()
+            assert abs(got.residual - ref.residual) <= 1e-5 * max(ref.residual, 1e-12)
+    al.SetSmLimit(0)
+    assert torch.equal(al.RunStepBatch(work), full)
+    with pytest.raises(Exception):
+        al.SetSmLimit(-1)
+
+
 @pytest.mark.parametrize("cs,w,h,mode", [(32, 320, 240, "auto"), (32, 320, 240, "fp32"), (8, 160, 120, "auto"),
                                          (16, 200, 96, "auto"), (64, 160, 120, "auto"), (128, 160, 120, "auto"),
                                          (32, 202, 96, "auto")])

@@ -12,7 +12,8 @@ import importlib
 __all__ = ["aligners", "synth", "se3", "SfmAligner", "SE3Aligner"]
 _LAZY = {"SfmAligner": "aligners", "SE3Aligner": "aligners", "DepthAligner": "aligners", "Window": "aligners", "SfmAlignerParams": "aligners",
          "DenseSfmParams": "aligners", "UpdateDepth": "aligners", "SobelGradients": "aligners",
-         "GaussianBlurDown": "aligners", "SquaredError": "aligners"}
+         "GaussianBlurDown": "aligners", "SquaredError": "aligners", "ReprojectionLinearize": "aligners",
+         "SparseGeometricLinearize": "aligners"}
 
 
 def __getattr__(name):

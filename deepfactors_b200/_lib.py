@@ -110,6 +110,8 @@ SYMBOLS = {
     "dfk_depth_run_step": (C.c_int, [_H, _F, C.c_int, _IMG, _IMG, _IMG, _F, _F, _F, C.POINTER(C.c_uint64)]),
     "dfk_reprojection_linearize": (C.c_int, [_H, _F, _F, _F, C.c_int, _CAM, _IMG, _IMG, C.c_int, _F, _F, C.c_float,
                                              C.c_float, _F, _F]),
+    "dfk_sparse_geometric_linearize": (C.c_int, [_H, _F, _F, _F, _F, C.c_int, _CAM, _IMG, _IMG, _IMG, _IMG, _IMG, C.c_int,
+                                                 C.POINTER(C.c_int), C.c_float, _F, C.POINTER(C.c_int)]),
     "dfk_update_depth": (C.c_int, [_H, _F, C.c_int, _IMG, _IMG, C.c_float, _IMG]),
     "dfk_sobel_gradients": (C.c_int, [_H, _IMG, _IMG]),
     "dfk_gaussian_blur_down": (C.c_int, [_H, _IMG, _IMG]),

@@ -288,6 +288,30 @@ def ReprojectionLinearize(aligner, pose0, pose1, code0, cam, prx_orig, prx_jac, 
     return rows, float(tot.value)
 
 
+def SparseGeometricLinearize(aligner, pose0, pose1, code0, code1, cam, prx0_orig, prx0_jac, prx1_orig, prx1_jac, dpt_grad1,
+                             points_xy, huber_delta: float):
+    """SparseGeometricFactor::linearize (sources/core/gtsam/sparse_geometric_factor.cpp:157-271) on the device: prx*_orig /
+    prx*_jac are the two keyframes' level-0 DEVICE buffers, dpt_grad1 keyframe 1's depth gradient [H, W, 2] (device),
+    points_xy the sampled integer pixels [M, 2] (host).  Returns (rows [M, 13 + 2C] float32 = the blocks of the
+    JacobianFactor [J_pose0 | J_pose1 | J_code0 | J_code1 | b], number of valid rows)."""
+    aligner._hd.use_torch_stream()
+    cs = aligner.CS
+    c0 = np.ascontiguousarray(code0, dtype=np.float32)
+    c1 = np.ascontiguousarray(code1, dtype=np.float32)
+    pts = np.ascontiguousarray(points_xy, dtype=np.int32).reshape(-1, 2)
+    M = pts.shape[0]
+    rows = np.zeros((M, 13 + 2 * cs), dtype=np.float32)
+    nv = C.c_int(0)
+    FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int)
+    c = _cam(cam)
+    i0, j0, i1, j1, g1 = _image(prx0_orig), _image(prx0_jac, cs), _image(prx1_orig), _image(prx1_jac, cs), _image(dpt_grad1, 2)
+    check(aligner.handle, lib().dfk_sparse_geometric_linearize(
+        aligner.handle, _pose(pose0), _pose(pose1), c0.ctypes.data_as(FP), c1.ctypes.data_as(FP), cs, C.byref(c), C.byref(i0),
+        C.byref(j0), C.byref(i1), C.byref(j1), C.byref(g1), M, pts.ctypes.data_as(IP), C.c_float(huber_delta),
+        rows.ctypes.data_as(FP), C.byref(nv)))
+    return rows, int(nv.value)
+
+
 # ------------------------------------------------------------------------------------------- DepthAligner
 class DepthAligner:
     """df::DepthAligner<float, CS> (sources/cuda/cu_depthaligner.h:38-54): code-only alignment of the decoded depth to a

@@ -1494,4 +1494,80 @@ DfkStatus dfk_reprojection_linearize(DfkHandle h, const float pose0[7], const fl
   }
 }
 
+DfkStatus dfk_sparse_geometric_linearize(DfkHandle h, const float pose0[7], const float pose1[7], const float* code0,
+                                         const float* code1, int code_size, const DfkCamera* cam, const DfkImage* prx0_orig,
+                                         const DfkImage* prx0_jac, const DfkImage* prx1_orig, const DfkImage* prx1_jac,
+                                         const DfkImage* dpt_grad1, int num_points, const int* points_xy, float huber_delta,
+                                         float* rows, int* num_valid)
+{
+  try {
+    if (!h) return DFK_ERR_INVALID_ARG;
+    if (!pose0 || !pose1 || !code0 || !code1 || !cam || !prx0_orig || !prx0_jac || !prx1_orig || !prx1_jac || !dpt_grad1 ||
+        !points_xy || !rows)
+      return fail(h, DFK_ERR_INVALID_ARG, "[SparseGeometricFactor::linearize] null argument");
+    if (!(code_size == 8 || code_size == 16 || code_size == 32 || code_size == 64 || code_size == 128))
+      return fail(h, DFK_ERR_UNSUPPORTED, "[SparseGeometricFactor::linearize] code size not instantiated: " + std::to_string(code_size));
+    if (num_points <= 0 || !(huber_delta > 0.0f))
+      return fail(h, DFK_ERR_INVALID_ARG, "[SparseGeometricFactor::linearize] no points / non-positive huber delta");
+    const uint32_t W = prx0_orig->width, H = prx0_orig->height;
+    if (W == 0 || H == 0 || !img_ok(prx0_orig, W, H, 1) || !img_ok(prx0_jac, W, H, code_size) || !img_ok(prx1_orig, W, H, 1) ||
+        !img_ok(prx1_jac, W, H, code_size) || !img_ok(dpt_grad1, W, H, 2))
+      return fail(h, DFK_ERR_INVALID_ARG, "[SparseGeometricFactor::linearize] inconsistent image views");
+    if (!cam_ok(cam, W, H))  // the nearest-neighbour lookups in keyframe 1 index with the camera's validity window
+      return fail(h, DFK_ERR_INVALID_ARG, "[SparseGeometricFactor::linearize] camera larger than the image views");
+    DeviceGuard guard(h->device);
+    const size_t M = (size_t)num_points, RW = 13 + 2 * (size_t)code_size;
+    const size_t n_in = 2 * M, n_out = M * RW;  // ints and floats are both 4 bytes
+    DFK_CUDA(h, ensure(&h->sparse_dev, &h->sparse_cap, n_in + n_out), "[SparseGeometricFactor::linearize] scratch allocation failed");
+    if (h->sparse_host_cap < n_in + n_out) {
+      if (h->sparse_host) cudaFreeHost(h->sparse_host);
+      h->sparse_host = nullptr;
+      h->sparse_host_cap = 0;
+      DFK_CUDA(h, cudaMallocHost((void**)&h->sparse_host, (n_in + n_out) * sizeof(float)),
+               "[SparseGeometricFactor::linearize] pinned allocation failed");
+      h->sparse_host_cap = n_in + n_out;
+    }
+    SparsePose sp;
+    float p10[7];
+    relative_pose(pose1, pose0, p10, sp.P1, sp.P0);  // RelativePose(p1, p0, pose10_J_pose1, pose10_J_pose0), :176-178
+    for (int k = 0; k < 4; ++k) sp.q[k] = p10[k];
+    for (int k = 0; k < 3; ++k) sp.t[k] = p10[4 + k];
+    quat_to_matrix(p10, sp.R);
+    sp.fx = cam->fx; sp.fy = cam->fy; sp.u0 = cam->u0; sp.v0 = cam->v0;
+    memcpy(h->sparse_host, points_xy, 2 * M * sizeof(int));
+    float codes[256] = {0};  // code_dev holds 256 floats: code0 at 0, code1 at 128
+    memcpy(codes, code0, sizeof(float) * code_size);
+    memcpy(codes + 128, code1, sizeof(float) * code_size);
+    int* d_points = reinterpret_cast<int*>(h->sparse_dev);
+    float* d_rows = h->sparse_dev + n_in;
+    DFK_CUDA(h, cudaMemcpyAsync(h->code_dev, codes, sizeof(codes), cudaMemcpyHostToDevice, h->stream),
+             "[SparseGeometricFactor::linearize] code upload failed");
+    DFK_CUDA(h, cudaMemcpyAsync(d_points, h->sparse_host, n_in * sizeof(float), cudaMemcpyHostToDevice, h->stream),
+             "[SparseGeometricFactor::linearize] point upload failed");
+    DFK_CUDA(h, launch_sparse_geometric_rows(sp, cam->width, cam->height, h->code_dev, h->code_dev + 128, code_size,
+                                             view_of(prx0_orig), view_of(prx0_jac), view_of(prx1_orig), view_of(prx1_jac),
+                                             view_of(dpt_grad1), (int)W, (int)H, num_points, d_points, huber_delta,
+                                             h->params.sfmparams.avg_dpt, d_rows, h->stream),
+             "[SparseGeometricFactor::linearize] kernel launch failed");
+    h->launches += 1;
+    DFK_CUDA(h, cudaMemcpyAsync(h->sparse_host + n_in, d_rows, n_out * sizeof(float), cudaMemcpyDeviceToHost, h->stream),
+             "[SparseGeometricFactor::linearize] result download failed");
+    DFK_CUDA(h, cudaStreamSynchronize(h->stream), "[SparseGeometricFactor::linearize] kernel launch failed");
+    memcpy(rows, h->sparse_host + n_in, n_out * sizeof(float));
+    if (num_valid) {
+      int nv = 0;
+      for (size_t i = 0; i < M; ++i) {
+        const float* r = rows + i * RW;
+        bool any = false;
+        for (size_t k = 0; k < RW && !any; ++k) any = r[k] != 0.0f;
+        nv += any ? 1 : 0;
+      }
+      *num_valid = nv;
+    }
+    return DFK_OK;
+  } catch (...) {
+    return oom(h);
+  }
+}
+
 }  // extern "C"

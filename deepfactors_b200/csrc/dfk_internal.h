@@ -172,6 +172,11 @@ cudaError_t launch_reprojection_rows(const SparsePose& sp, const float* code_dev
                                      float cauchy_delta, float sigma, float avg_dpt, float* rows_dev, float* err2_dev,
                                      cudaStream_t s);
 
+cudaError_t launch_sparse_geometric_rows(const SparsePose& sp, float cam_w, float cam_h, const float* code0_dev,
+                                         const float* code1_dev, int code_size, View prx0, View jac0, View prx1, View jac1,
+                                         View grad1, int width, int height, int num_points, const int* points_dev,
+                                         float huber_delta, float avg_dpt, float* rows_dev, cudaStream_t s);
+
 constexpr int kSimpleMaxBlocks = 1024;
 constexpr int kSimpleScratchFloats = kSimpleMaxBlocks * 32;
 

@@ -1,4 +1,5 @@
-// dfk_sparse.cu -- ReprojectionFactor::linearize on the device (sources/core/gtsam/reprojection_factor.cpp:157-269).
+// dfk_sparse.cu -- the sparse factors on the device: ReprojectionFactor::linearize
+// (sources/core/gtsam/reprojection_factor.cpp:157-269) and SparseGeometricFactor::linearize (second half of the file).
 //
 // The reference evaluates this sparse keypoint factor on the CPU and, to read the code Jacobian at <= a few thousand
 // keypoints, forces a device -> host mirror of the keyframe's WHOLE level-0 code-Jacobian pyramid
@@ -106,6 +107,94 @@ reprojection_rows_kernel(SparsePose sp, const float* __restrict__ code, View prx
   err2[i] = err * err;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// SparseGeometricFactor::linearize (sources/core/gtsam/sparse_geometric_factor.cpp:157-271): one row per sampled pixel of
+// keyframe 0 -- the depth keyframe 1 decodes at the (nearest-neighbour) correspondence against the depth of the warped
+// point.  The reference runs it on the CPU over host mirrors of BOTH keyframes' level-0 proximity / code-Jacobian
+// pyramids and of kf1's depth gradient (:181-183, :207-209, :220).  One thread per point:
+//   dpt0   = DepthFromCode(c0, prx0_J_cde, prx0_0code, avg_dpt)                                   :186
+//   corr   = FindCorrespondence(pt, dpt0, cam, pose10)  (border 1, min_dpt 0, bounds checked)     :187-198
+//   dpt1_p = corr.tpt.z ; pix1_nn = (int) corr.pix1 ; dpt1 = DepthFromCode(c1, kf1 @ pix1_nn)      :201-210
+//   err    = dpt1 - dpt1_p                                                                         :213
+//   J_pose0/1 = ( TransformJacobianPose.row(2) - dpt_grad * corr_J_pose10 ) * pose10_J_pose0/1     :223-238
+//   J_cde0 = (R ray).z * DepthJacobianPrx(dpt0) * prx0_J_cde - dpt_grad * corr_J_cde0              :241-246
+//   J_cde1 = -DepthJacobianPrx(dpt1) * prx1_J_cde                                                  :249
+//   everything * HuberWeight(err, huber_delta)                                                     :252-258
+// The decode and the validity chain use round-to-nearest intrinsics in the reference's operation order (as the dense
+// kernels do), so the set of valid rows and the nearest-neighbour pixels are those of the CPU evaluation.
+template <int C>
+__global__ void __launch_bounds__(128)
+sparse_geometric_rows_kernel(SparsePose sp, float cam_w, float cam_h, const float* __restrict__ code0,
+                             const float* __restrict__ code1, View prx0, View jac0, View prx1, View jac1, View grad1, int width,
+                             int height, int num_points, const int2* __restrict__ points, float huber_delta, float avg_dpt,
+                             float* __restrict__ rows)
+{
+  constexpr int RW = 13 + 2 * C;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_points) return;
+  float* r = rows + (size_t)i * RW;
+  const int2 pt = points[i];
+  bool valid = pt.x >= 0 && pt.y >= 0 && pt.x < width && pt.y < height;  // the reference would read out of bounds
+  Warped w;
+  w.valid = false;
+  float dpt0 = 0.0f;
+  const float* jr0 = nullptr;
+  if (valid) {
+    jr0 = jac0.ptr + (size_t)pt.y * jac0.pitch + (size_t)pt.x * C;
+    float dot = 0.0f;
+    for (int k = 0; k < C; ++k) dot = __fadd_rn(dot, __fmul_rn(__ldg(jr0 + k), code0[k]));  // (prx_J_cde * code)(0), left to right
+    dpt0 = prx_to_depth(__fadd_rn(__ldg(prx0.ptr + (size_t)pt.y * prx0.pitch + pt.x), dot), avg_dpt);
+    w = warp_pixel((float)pt.x, (float)pt.y, dpt0, sp.q, sp.t, sp.fx, sp.fy, sp.u0, sp.v0, 1.0f, __fsub_rn(cam_w, 1.0f),
+                   __fsub_rn(cam_h, 1.0f), 0.0f);
+    valid = w.valid;
+  }
+  if (!valid) {
+    for (int k = 0; k < RW; ++k) r[k] = 0.0f;
+    return;
+  }
+  const int nx = (int)w.u, ny = (int)w.v;  // pix1.cast<int>()
+  const float* jr1 = jac1.ptr + (size_t)ny * jac1.pitch + (size_t)nx * C;
+  float dot1 = 0.0f;
+  for (int k = 0; k < C; ++k) dot1 = __fadd_rn(dot1, __fmul_rn(__ldg(jr1 + k), code1[k]));
+  const float dpt1 = prx_to_depth(__fadd_rn(__ldg(prx1.ptr + (size_t)ny * prx1.pitch + nx), dot1), avg_dpt);
+  const float err = __fsub_rn(dpt1, w.tz);
+  const float g0 = __ldg(grad1.ptr + (size_t)ny * grad1.pitch + 2 * nx), g1 = __ldg(grad1.ptr + (size_t)ny * grad1.pitch + 2 * nx + 1);
+  const float X = w.tx, Y = w.ty, Z = w.tz;
+  const float c00 = sp.fx / Z, c02 = -(sp.fx * X) / Z / Z, c11 = sp.fy / Z, c12 = -(sp.fy * Y) / Z / Z;  // ProjectPointJacobian
+  const float A0[6] = {c00, 0.f, c02, c02 * w.py, c00 * w.pz - c02 * w.px, -(c00 * w.py)};  // corr_J_pose10 = dCam [I | -hat(R pt)]
+  const float A1[6] = {0.f, c11, c12, c12 * w.py - c11 * w.pz, -(c12 * w.px), c11 * w.px};
+  const float T2[6] = {0.f, 0.f, 1.f, w.py, -w.px, 0.f};  // row 2 of TransformJacobianPose
+  float B[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) B[k] = T2[k] - (g0 * A0[k] + g1 * A1[k]);
+  const float hw = huber_weight(err, huber_delta);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      s0 += B[k] * sp.P0[k * 6 + j];
+      s1 += B[k] * sp.P1[k * 6 + j];
+    }
+    r[j] = s0 * hw;
+    r[6 + j] = s1 * hw;
+  }
+  // pix1_J_dpt = dCam * R * ray ; (R ray).z ; dpt_J_prx = -avg / prx^2
+  const float q0 = sp.R[0] * w.xn + sp.R[1] * w.yn + sp.R[2];
+  const float q1 = sp.R[3] * w.xn + sp.R[4] * w.yn + sp.R[5];
+  const float q2 = sp.R[6] * w.xn + sp.R[7] * w.yn + sp.R[8];
+  const float pr0 = avg_dpt / (avg_dpt + dpt0), dJ0 = -avg_dpt / (pr0 * pr0);
+  const float jd0 = (c00 * q0 + c02 * q2) * dJ0, jd1 = (c11 * q1 + c12 * q2) * dJ0;
+  const float e0 = (q2 * dJ0 - (g0 * jd0 + g1 * jd1)) * hw;
+  const float pr1 = avg_dpt / (avg_dpt + dpt1), dJ1 = -avg_dpt / (pr1 * pr1);
+  const float e1 = -dJ1 * hw;
+  for (int k = 0; k < C; ++k) {
+    r[12 + k] = e0 * __ldg(jr0 + k);
+    r[12 + C + k] = e1 * __ldg(jr1 + k);
+  }
+  r[12 + 2 * C] = err * hw;
+}
+
 }  // namespace
 
 cudaError_t launch_reprojection_rows(const SparsePose& sp, const float* code_dev, int code_size, View prx_orig, View jac,
@@ -130,6 +219,31 @@ cudaError_t launch_reprojection_rows(const SparsePose& sp, const float* code_dev
     default: return cudaErrorInvalidValue;
   }
 #undef DFK_SP
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sparse_geometric_rows(const SparsePose& sp, float cam_w, float cam_h, const float* code0_dev,
+                                         const float* code1_dev, int code_size, View prx0, View jac0, View prx1, View jac1,
+                                         View grad1, int width, int height, int num_points, const int* points_dev,
+                                         float huber_delta, float avg_dpt, float* rows_dev, cudaStream_t s)
+{
+  const int blocks = (num_points + 127) / 128;
+  const int2* pts = reinterpret_cast<const int2*>(points_dev);
+#define DFK_SG(CS)                                                                                                        \
+  case CS:                                                                                                                \
+    sparse_geometric_rows_kernel<CS><<<blocks, 128, 0, s>>>(sp, cam_w, cam_h, code0_dev, code1_dev, prx0, jac0, prx1, jac1, \
+                                                            grad1, width, height, num_points, pts, huber_delta, avg_dpt,  \
+                                                            rows_dev);                                                    \
+    break;
+  switch (code_size) {
+    DFK_SG(8)
+    DFK_SG(16)
+    DFK_SG(32)
+    DFK_SG(64)
+    DFK_SG(128)
+    default: return cudaErrorInvalidValue;
+  }
+#undef DFK_SG
   return cudaGetLastError();
 }
 

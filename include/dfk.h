@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define DFK_VERSION 103
+#define DFK_VERSION 104
 
 typedef enum {
   DFK_OK = 0,
@@ -317,6 +317,23 @@ DfkStatus dfk_reprojection_linearize(DfkHandle h, const float pose0[7], const fl
                                      const DfkImage* prx_jac, int num_matches, const float* query_xy,
                                      const float* train_xy, float cauchy_delta, float sigma, float* rows,
                                      float* total_err);
+
+/* SparseGeometricFactor::linearize (sources/core/gtsam/sparse_geometric_factor.cpp:157-271): the Jacobian rows of the
+ * sparse depth-consistency factor between two keyframes, evaluated on the device from the keyframes' level-0 proximity /
+ * code-Jacobian buffers and keyframe 1's depth gradient instead of host mirrors of all five (:181-183, :207-209, :220).
+ *   points_xy    HOST, 2 ints per point: the sampled pixels of keyframe 0 (UniformSampler, uniform_sampler.h:28-32)
+ *   dpt_grad1    kf1->dpt_grad: SobelGradients of keyframe 1's level-0 depth (mapper.cpp:998-1000), 2 floats per pixel
+ *   rows         HOST out, num_points x (13 + 2 * code_size), row-major:
+ *                [dErr/dPose0 (6) | dErr/dPose1 (6) | dErr/dCode0 (C) | dErr/dCode1 (C) | b], already multiplied by the
+ *                Huber weight (DenseSfm_RobustLoss, dense_sfm.h:47-50) -- the blocks of gtsam::JacobianFactor(keys, Ab)
+ *                (:260-270); zero rows for points whose correspondence is invalid (:190-198)
+ *   num_valid    out (may be NULL): rows that are not all zero
+ * avg_dpt is hard-coded to 2 there (:166); here it is the handle's DenseSfmParams::avg_dpt.  Synchronous. */
+DfkStatus dfk_sparse_geometric_linearize(DfkHandle h, const float pose0[7], const float pose1[7], const float* code0,
+                                         const float* code1, int code_size, const DfkCamera* cam, const DfkImage* prx0_orig,
+                                         const DfkImage* prx0_jac, const DfkImage* prx1_orig, const DfkImage* prx1_jac,
+                                         const DfkImage* dpt_grad1, int num_points, const int* points_xy, float huber_delta,
+                                         float* rows, int* num_valid);
 
 /* ------------------------------------------------------------------ cu_image_proc free functions */
 

@@ -185,6 +185,22 @@ double dfko_reprojection_rows_d(const float pose0[7], const float pose1[7], cons
                                 const float* prx_jac, size_t jac_pitch, int num_matches, const float* query_xy,
                                 const float* train_xy, float cauchy_delta, float sigma, float avg_dpt, double* rows_out);
 
+/* ---- SparseGeometricFactor::linearize rows (core/gtsam/sparse_geometric_factor.cpp:157-271): rows_out is
+ * num_points x (13 + 2C) row-major [J_pose0 | J_pose1 | J_code0 | J_code1 | b] (Huber-weighted); returns the number of
+ * valid rows.  points_xy: 2 ints per point; dpt_grad1: (gx, gy) interleaved Sobel gradient of keyframe 1's depth */
+int dfko_sparse_geometric_rows_f(const float pose0[7], const float pose1[7], const float* code0, const float* code1,
+                                 int code_size, const DfkoCamera* cam, int width, int height, const float* prx0_orig,
+                                 size_t prx0_pitch, const float* jac0, size_t jac0_pitch, const float* prx1_orig,
+                                 size_t prx1_pitch, const float* jac1, size_t jac1_pitch, const float* dpt_grad1,
+                                 size_t grad_pitch, int num_points, const int* points_xy, float huber_delta, float avg_dpt,
+                                 float* rows_out);
+int dfko_sparse_geometric_rows_d(const float pose0[7], const float pose1[7], const float* code0, const float* code1,
+                                 int code_size, const DfkoCamera* cam, int width, int height, const float* prx0_orig,
+                                 size_t prx0_pitch, const float* jac0, size_t jac0_pitch, const float* prx1_orig,
+                                 size_t prx1_pitch, const float* jac1, size_t jac1_pitch, const float* dpt_grad1,
+                                 size_t grad_pitch, int num_points, const int* points_xy, float huber_delta, float avg_dpt,
+                                 double* rows_out);
+
 /* ---- pyramid construction (cu_image_proc.cpp:57-92, 134-164) and SquaredError (:190-242) */
 void dfko_sobel_gradients_f(int width, int height, const float* img, size_t img_pitch,
                             float* grad /* (gx,gy) interleaved */, size_t grad_pitch);

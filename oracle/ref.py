@@ -164,6 +164,30 @@ def reprojection_rows(pose0, pose1, code, cam, prx_orig, prx_jac, query_xy, trai
     return rows, float(tot)
 
 
+def sparse_geometric_rows(pose0, pose1, code0, code1, cam, prx0_orig, prx0_jac, prx1_orig, prx1_jac, dpt_grad1, points_xy,
+                          huber_delta, avg_dpt=2.0):
+    code0 = np.ascontiguousarray(code0, dtype=np.float32)
+    code1 = np.ascontiguousarray(code1, dtype=np.float32)
+    prx0_orig, prx0_jac, prx1_orig, prx1_jac, dpt_grad1 = map(_f32, (prx0_orig, prx0_jac, prx1_orig, prx1_jac, dpt_grad1))
+    H, W = prx0_orig.shape
+    Cs = code0.shape[0]
+    pts = np.ascontiguousarray(points_xy, dtype=np.int32).reshape(-1, 2)
+    M = pts.shape[0]
+    pose0 = np.ascontiguousarray(pose0, dtype=np.float32)
+    pose1 = np.ascontiguousarray(pose1, dtype=np.float32)
+    c = _cam(cam)
+    rows = np.zeros((M, 13 + 2 * Cs), dtype=np.float32)
+    fn = lib().dfkr_sparse_geometric_rows_f
+    fn.restype = C.c_int
+    n = fn(_ptr(pose0), _ptr(pose1), _ptr(code0), _ptr(code1), C.c_int(Cs), C.byref(c), C.c_int(W), C.c_int(H),
+           _ptr(prx0_orig), _pitch(prx0_orig), _ptr(prx0_jac), _pitch(prx0_jac), _ptr(prx1_orig), _pitch(prx1_orig),
+           _ptr(prx1_jac), _pitch(prx1_jac), _ptr(dpt_grad1), _pitch(dpt_grad1), C.c_int(M),
+           pts.ctypes.data_as(C.POINTER(C.c_int)), C.c_float(huber_delta), C.c_float(avg_dpt), _ptr(rows))
+    if n < 0:
+        raise ValueError("code size not instantiated")
+    return rows, int(n)
+
+
 def update_depth(code, prx_orig, prx_jac, avg_dpt=2.0):
     code = np.ascontiguousarray(code, dtype=np.float32)
     prx_orig, prx_jac = _f32(prx_orig), _f32(prx_jac)

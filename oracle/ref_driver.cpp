@@ -220,6 +220,84 @@ float reprojection_rows(const float* pose0, const float* pose1, const float* cod
   return total_err;
 }
 
+// SparseGeometricFactor::linearize's rows (core/gtsam/sparse_geometric_factor.cpp:157-271) over the reference's own
+// warping.h / dense_sfm.h / pinhole_camera.h functions (the factor itself needs GTSAM and the Keyframe class): every
+// statement between the lookup of the point and the fill of Ab, in the reference's order.  dpt_grad1 = kf1->dpt_grad
+// (mapper.cpp:998-1000: SobelGradients of the keyframe's level-0 depth), 2 floats per pixel.
+template <int CS>
+int sparse_geometric_rows(const float* pose0, const float* pose1, const float* code0_in, const float* code1_in, const Cam6* c,
+                          int width, int height, const float* prx0_orig, size_t prx0_pitch, const float* jac0, size_t jac0_pitch,
+                          const float* prx1_orig, size_t prx1_pitch, const float* jac1, size_t jac1_pitch,
+                          const float* dpt_grad1, size_t grad_pitch, int num_points, const int* points_xy, float huber_delta_,
+                          float avg_dpt, float* rows)
+{
+  using Scalar = float;
+  const int RW = 13 + 2 * CS;
+  const Sophus::SE3f p0 = make_se3(pose0), p1 = make_se3(pose1);
+  const df::PinholeCamera<float> cam_(c->fx, c->fy, c->u0, c->v0, c->width, c->height);
+  Eigen::Matrix<Scalar, CS, 1> c0, c1;
+  for (int k = 0; k < CS; ++k) { c0(k) = code0_in[k]; c1(k) = code1_in[k]; }
+  const ImgView prx0_img = view(prx0_orig, width, height, prx0_pitch);
+  const ImgView prx1_img = view(prx1_orig, width, height, prx1_pitch);
+  ImgView prx0_jac_img(const_cast<float*>(jac0), (size_t)width * CS, (size_t)height, jac0_pitch * sizeof(float));
+  ImgView prx1_jac_img(const_cast<float*>(jac1), (size_t)width * CS, (size_t)height, jac1_pitch * sizeof(float));
+  int valid_rows = 0;
+  for (int i = 0; i < num_points; ++i) {
+    float* r = rows + (size_t)i * RW;
+    for (int k = 0; k < RW; ++k) r[k] = 0;
+    const int ptx = points_xy[2 * i], pty = points_xy[2 * i + 1];
+    if (ptx < 0 || pty < 0 || ptx >= width || pty >= height) continue;
+    Eigen::Matrix<Scalar, 6, 6> pose10_J_pose0;
+    Eigen::Matrix<Scalar, 6, 6> pose10_J_pose1;
+    Sophus::SE3f pose10 = df::RelativePose(p1, p0, pose10_J_pose1, pose10_J_pose0);
+    Eigen::Map<const Eigen::Matrix<Scalar, 1, CS>> tmp0(&prx0_jac_img(ptx * CS, pty));
+    const Eigen::Matrix<Scalar, 1, CS> prx0_J_cde(tmp0);
+    Scalar prx0_0code = prx0_img(ptx, pty);
+    Scalar dpt0 = df::DepthFromCode(c0, prx0_J_cde, prx0_0code, avg_dpt);
+    df::Correspondence<Scalar> corr = df::FindCorrespondence((std::size_t)ptx, (std::size_t)pty, dpt0, cam_, pose10);
+    if (!cam_.PixelValid(corr.pix1) || !corr.valid) continue;
+    Scalar dpt1_p = corr.tpt(2);
+    const int nn0 = (int)corr.pix1(0), nn1 = (int)corr.pix1(1);  // pix1.cast<int>()
+    Eigen::Map<const Eigen::Matrix<Scalar, 1, CS>> tmp1(&prx1_jac_img(nn0 * CS, nn1));
+    const Eigen::Matrix<Scalar, 1, CS> prx1_J_cde(tmp1);
+    Scalar prx1_0code = prx1_img(nn0, nn1);
+    Scalar dpt1 = df::DepthFromCode(c1, prx1_J_cde, prx1_0code, avg_dpt);
+    Scalar err = dpt1 - dpt1_p;
+    Eigen::Matrix<Scalar, 1, 2> dpt_grad;
+    dpt_grad(0, 0) = dpt_grad1[(size_t)nn1 * grad_pitch + 2 * nn0];
+    dpt_grad(0, 1) = dpt_grad1[(size_t)nn1 * grad_pitch + 2 * nn0 + 1];
+    Eigen::Matrix<Scalar, 2, 6> corr_J_pose10 = df::FindCorrespondenceJacobianPose(corr, dpt0, cam_, pose10);
+    Eigen::Matrix<Scalar, 3, 6> tpt_J_pose0 = df::TransformJacobianPose(corr.pt, pose10) * pose10_J_pose0;
+    const Eigen::Matrix<Scalar, 3, 6>& tpt_J_pose0_c = tpt_J_pose0;
+    Eigen::Matrix<Scalar, 1, 6> dpt1p_J_pose0 = tpt_J_pose0_c.template block<1, 6>(2, 0);
+    Eigen::Matrix<Scalar, 1, 6> g_pose10 = dpt_grad * corr_J_pose10;
+    Eigen::Matrix<Scalar, 1, 6> err_J_pose0 = dpt1p_J_pose0 - g_pose10 * pose10_J_pose0;
+    Eigen::Matrix<Scalar, 3, 6> tpt_J_pose1 = df::TransformJacobianPose(corr.pt, pose10) * pose10_J_pose1;
+    const Eigen::Matrix<Scalar, 3, 6>& tpt_J_pose1_c = tpt_J_pose1;
+    Eigen::Matrix<Scalar, 1, 6> dpt1p_J_pose1 = tpt_J_pose1_c.template block<1, 6>(2, 0);
+    Eigen::Matrix<Scalar, 1, 6> err_J_pose1 = dpt1p_J_pose1 - g_pose10 * pose10_J_pose1;
+    Eigen::Matrix<Scalar, 2, CS> corr_J_cde0;
+    df::FindCorrespondenceJacobianCode(corr, dpt0, cam_, pose10, prx0_J_cde, avg_dpt, corr_J_cde0);
+    Eigen::Matrix<Scalar, 3, 3> trans_J_pt = df::TransformJacobianPoint(corr.pt, pose10);
+    Eigen::Matrix<Scalar, 3, 1> trans_J_dpt = trans_J_pt * cam_.ReprojectDepthJacobian(corr.pix0, dpt0);
+    Eigen::Matrix<Scalar, 3, CS> trans_J_cde = (trans_J_dpt * df::DepthJacobianPrx(dpt0, avg_dpt)) * prx0_J_cde;
+    const Eigen::Matrix<Scalar, 3, CS>& trans_J_cde_c = trans_J_cde;  // the shim's non-const block() is an assignable view
+    Eigen::Matrix<Scalar, 1, CS> err_J_cde0 = trans_J_cde_c.template block<1, CS>(2, 0) - dpt_grad * corr_J_cde0;
+    Eigen::Matrix<Scalar, 1, CS> err_J_cde1 = prx1_J_cde * (-df::DepthJacobianPrx(dpt1, avg_dpt));
+    Scalar hbr_wgt = df::DenseSfm_RobustLoss(err, huber_delta_);
+    err *= hbr_wgt;
+    err_J_pose0 *= hbr_wgt;
+    err_J_pose1 *= hbr_wgt;
+    err_J_cde0 *= hbr_wgt;
+    err_J_cde1 *= hbr_wgt;
+    for (int j = 0; j < 6; ++j) { r[j] = err_J_pose0(0, j); r[6 + j] = err_J_pose1(0, j); }
+    for (int k = 0; k < CS; ++k) { r[12 + k] = err_J_cde0(0, k); r[12 + CS + k] = err_J_cde1(0, k); }
+    r[12 + 2 * CS] = err;
+    ++valid_rows;
+  }
+  return valid_rows;
+}
+
 }  // namespace
 
 extern "C" {
@@ -425,6 +503,22 @@ float dfkr_reprojection_rows_f(const float pose0[7], const float pose1[7], const
     case 8: return reprojection_rows<8>(pose0, pose1, code, cam, width, height, prx_orig, prx_pitch, prx_jac, jac_pitch, num_matches, query_xy, train_xy, cauchy_delta, sigma, avg_dpt, rows);
     case 32: return reprojection_rows<32>(pose0, pose1, code, cam, width, height, prx_orig, prx_pitch, prx_jac, jac_pitch, num_matches, query_xy, train_xy, cauchy_delta, sigma, avg_dpt, rows);
     default: return -1.0f;
+  }
+}
+
+// SparseGeometricFactor::linearize's rows; returns the number of non-zero (valid) rows, -1 if the code size is not
+// instantiated
+int dfkr_sparse_geometric_rows_f(const float pose0[7], const float pose1[7], const float* code0, const float* code1,
+                                 int code_size, const Cam6* cam, int width, int height, const float* prx0_orig,
+                                 size_t prx0_pitch, const float* jac0, size_t jac0_pitch, const float* prx1_orig,
+                                 size_t prx1_pitch, const float* jac1, size_t jac1_pitch, const float* dpt_grad1,
+                                 size_t grad_pitch, int num_points, const int* points_xy, float huber_delta, float avg_dpt,
+                                 float* rows)
+{
+  switch (code_size) {
+    case 8: return sparse_geometric_rows<8>(pose0, pose1, code0, code1, cam, width, height, prx0_orig, prx0_pitch, jac0, jac0_pitch, prx1_orig, prx1_pitch, jac1, jac1_pitch, dpt_grad1, grad_pitch, num_points, points_xy, huber_delta, avg_dpt, rows);
+    case 32: return sparse_geometric_rows<32>(pose0, pose1, code0, code1, cam, width, height, prx0_orig, prx0_pitch, jac0, jac0_pitch, prx1_orig, prx1_pitch, jac1, jac1_pitch, dpt_grad1, grad_pitch, num_points, points_xy, huber_delta, avg_dpt, rows);
+    default: return -1;
   }
 }
 

@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol():
 def test_non_compute_calls_work_without_a_gpu():
     from deepfactors_b200 import _lib
     L = _lib.lib()
-    assert L.dfk_version() == 103  # DFK_VERSION of include/dfk.h
+    assert L.dfk_version() == 104  # DFK_VERSION of include/dfk.h
     assert L.dfk_status_string(0) == b"ok"
     assert L.dfk_sfm_supports_code_size(32) == 1
     assert L.dfk_sfm_supports_code_size(64) == 1 and L.dfk_sfm_supports_code_size(128) == 1

@@ -667,3 +667,34 @@ def test_reprojection_factor_rows_on_device_match_oracle(oracle, cs):
     assert rows.shape == r64.shape and not rows[6:8].any()
     assert np.abs(rows - r64).max() <= 1e-4 * np.abs(r64).max()
     assert abs(tot - e64) <= 1e-4 * e64
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cs", [32, 8])
+def test_sparse_geometric_factor_rows_on_device_match_oracle(oracle, cs):
+    """dfk_sparse_geometric_linearize (sparse_geometric_factor.cpp:157-271 on the device) vs the CPU oracle: the same set
+    of valid rows (exact-order decode + validity chain), every block of the rows within fp32 rounding of the fp64 oracle"""
+    import torch
+    from deepfactors_b200.aligners import SfmAligner, SparseGeometricLinearize
+    from test_oracle_ref import _geometric_scene
+    L0, L1, code0, code1, g1, pts = _geometric_scene(cs)
+    pts = np.concatenate([pts, np.array([[-3, 5], [200, 10]], dtype=np.int32)])   # outside the image: zero rows
+    pose0, pose1 = synth.reference_test_poses()
+    al = SfmAligner(cs)
+    rows, nv = SparseGeometricLinearize(al, pose0, pose1, code0, code1, L0.cam, pitched(torch, L0.prx_orig, 3),
+                                        pitched(torch, L0.prx_jac, 2), pitched(torch, L1.prx_orig, 1),
+                                        pitched(torch, L1.prx_jac, 4), pitched(torch, g1, 2), pts, 0.1)
+    args = (pose0, pose1, code0, code1, L0.cam, L0.prx_orig, L0.prx_jac, L1.prx_orig, L1.prx_jac, g1, pts, 0.1)
+    r32, n32 = oracle.sparse_geometric_rows(*args)
+    r64, n64 = oracle.sparse_geometric_rows(*args, precision="f64")
+    assert rows.shape == r64.shape and not rows[-2:].any()
+    assert nv == n32 and 0 < nv < pts.shape[0]
+    assert np.array_equal(np.abs(rows).sum(1) > 0, np.abs(r32).sum(1) > 0), "valid set differs from the fp32 CPU path"
+    same = (np.abs(r64).sum(1) > 0) == (np.abs(r32).sum(1) > 0)   # fp64 may disagree on a point that sits on the border
+    for sl in (slice(0, 6), slice(6, 12), slice(12, 12 + cs), slice(12 + cs, 12 + 2 * cs), slice(12 + 2 * cs, None)):
+        assert np.abs(rows[same][:, sl] - r64[same][:, sl]).max() <= 2e-4 * np.abs(r64[:, sl]).max()
+    # loud errors
+    with pytest.raises(Exception):
+        SparseGeometricLinearize(al, pose0, pose1, code0, code1, L0.cam, pitched(torch, L0.prx_orig, 3),
+                                 pitched(torch, L0.prx_jac, 2), pitched(torch, L1.prx_orig[:-2], 1),
+                                 pitched(torch, L1.prx_jac, 4), pitched(torch, g1, 2), pts, 0.1)

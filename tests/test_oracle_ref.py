@@ -219,3 +219,68 @@ def test_reprojection_factor_marks_points_behind_the_camera(oracle):
     ro, eo = oracle.reprojection_rows(pose0, pose1, code, L.cam, L.prx_orig, L.prx_jac, q, t, 1.0, 1.0)
     rr, er = ref.reprojection_rows(pose0, pose1, code, L.cam, L.prx_orig, L.prx_jac, q, t, 1.0, 1.0)
     assert not ro.any() and not rr.any() and eo == er == 0.0
+
+
+def _geometric_scene(cs, w=160, h=120):
+    """two keyframes of one scene for the sparse geometric factor: kf0 / kf1 with their own proximity + code Jacobian, codes,
+    and kf1's depth gradient (mapper.cpp:998-1000: Sobel of its level-0 depth)"""
+    L0 = synth.make_level(w, h, cs, seed=21)
+    L1 = synth.make_level(w, h, cs, seed=22, phase=0.3)
+    rng = np.random.default_rng(9)
+    code0 = (rng.standard_normal(cs) * 0.3).astype(np.float32)
+    code1 = (rng.standard_normal(cs) * 0.3).astype(np.float32)
+    prx1 = L1.prx_orig + (L1.prx_jac @ code1).astype(np.float32)
+    dpt1 = (np.float32(2.0) / prx1 - np.float32(2.0)).astype(np.float32)
+    dpt_grad1 = synth.sobel_np(dpt1)
+    ys, xs = np.mgrid[3:h - 3:7, 3:w - 3:9]
+    pts = np.stack([xs.ravel(), ys.ravel()], 1).astype(np.int32)   # UniformSampler's role: integer pixels (uniform_sampler.h:28-32)
+    return L0, L1, code0, code1, dpt_grad1, pts
+
+
+def test_sparse_geometric_factor_rows_oracle_equals_reference_headers(oracle):
+    # core/gtsam/sparse_geometric_factor.cpp:171-266 around the reference's own warping.h / dense_sfm.h / pinhole_camera.h
+    cs = 32
+    L0, L1, code0, code1, g1, pts = _geometric_scene(cs)
+    pose0, pose1 = synth.reference_test_poses()
+    args = (pose0, pose1, code0, code1, L0.cam, L0.prx_orig, L0.prx_jac, L1.prx_orig, L1.prx_jac, g1, pts, 0.1)
+    ro, no = oracle.sparse_geometric_rows(*args)
+    rr, nr = ref.sparse_geometric_rows(*args)
+    assert ro.shape == rr.shape == (pts.shape[0], 13 + 2 * cs)
+    assert no == nr and 0 < nr < pts.shape[0], "some points must warp out of the frame, most must not"
+    assert np.array_equal(np.abs(ro).sum(1) > 0, np.abs(rr).sum(1) > 0)
+    for sl in (slice(0, 6), slice(6, 12), slice(12, 12 + cs), slice(12 + cs, 12 + 2 * cs), slice(12 + 2 * cs, None)):
+        assert np.abs(ro[:, sl] - rr[:, sl]).max() <= 5e-5 * np.abs(rr[:, sl]).max()
+    r64, n64 = oracle.sparse_geometric_rows(*args, precision="f64")
+    assert n64 == nr
+    assert np.abs(rr - r64).max() <= 2e-4 * np.abs(r64).max()
+
+
+def test_sparse_geometric_factor_rows_are_the_derivative_of_the_residual(oracle):
+    """finite differences of b = w (dpt1 - dpt1') with the Huber weight frozen (huge delta: w = 1): the JacobianFactor
+    convention is |A dx - b|, so A = -d b / d x for the code of keyframe 1, whose pixel lookup does not move with it"""
+    cs = 8
+    L0, L1, code0, code1, g1, pts = _geometric_scene(cs, 96, 72)
+    pose0, pose1 = synth.reference_test_poses()
+    base = (pose0, pose1, code0, code1, L0.cam, L0.prx_orig, L0.prx_jac, L1.prx_orig, L1.prx_jac, g1, pts, 1e9)
+    r, n = oracle.sparse_geometric_rows(*base, precision="f64")
+    assert n > 10
+    ok = np.abs(r).sum(1) > 0
+    eps = 1e-3
+    for k in (0, 5):
+        c1 = code1.astype(np.float64).copy(); c1[k] += eps
+        rp, _ = oracle.sparse_geometric_rows(pose0, pose1, code0, c1.astype(np.float32), *base[4:], precision="f64")
+        fd = (rp[ok, -1] - r[ok, -1]) / eps              # d b / d code1_k
+        assert np.abs(fd + r[ok, 12 + cs + k]).max() <= 2e-3 * np.abs(r[ok, 12 + cs + k]).max()
+
+
+def test_sparse_geometric_factor_invalid_points_give_zero_rows(oracle):
+    cs = 8
+    L0, L1, code0, code1, g1, _ = _geometric_scene(cs, 80, 60)
+    pose0 = synth.se3.identity()
+    pose1 = synth.se3.make_pose([0, 0, 0], [0, 0, 30.0], np.float32)   # every point ends up behind the second camera
+    pts = np.array([[10, 12], [40, 30], [-1, 5], [79, 59]], dtype=np.int32)
+    ro, no = oracle.sparse_geometric_rows(pose0, pose1, code0, code1, L0.cam, L0.prx_orig, L0.prx_jac, L1.prx_orig, L1.prx_jac,
+                                          g1, pts, 0.1)
+    rr, nr = ref.sparse_geometric_rows(pose0, pose1, code0, code1, L0.cam, L0.prx_orig, L0.prx_jac, L1.prx_orig, L1.prx_jac,
+                                       g1, pts, 0.1)
+    assert no == nr == 0 and not ro.any() and not rr.any()

@@ -17,7 +17,8 @@
 //   operand, no transposition and no tile staging any more: a front-end warp goes from global memory to a finished
 //   operand block on its own and hands it to the MMA issuer with one mbarrier arrival.
 //
-//   Per CTA (512 threads, 2 CTAs / SM, 128 TMEM columns each; register budgets by setmaxnreg):
+//   Per CTA (512 threads, 2 CTAs / SM, 128 TMEM columns each; the drain / control warpgroup gives registers back with
+//   setmaxnreg -- ptxas allocates for the launch bound, 64 registers, whatever setmaxnreg.inc says afterwards):
 //     warps 0-11  front-end : warp w owns the CTA's 32-pixel blocks j = w, w+12, ... (a 128-pixel tile = 4 blocks).
 //                             One thread per pixel: (optional depth decode,) exact-order validity chain, bilinear
 //                             gathers, Jacobian row, Huber -> s = w*e, w*a[6], w*diff.  Then the block's code-Jacobian
@@ -29,11 +30,13 @@
 //                             pixel are skipped altogether (no loads, no MMA).
 //     warps 12-14 drain     : pull a finished accumulation chain out of TMEM (tcgen05.ld) and add it in round-to-nearest
 //                             fp32 to the CTA's partial in global memory (single writer per address, program order).
-//     warp 15     control   : lane 0 walks the blocks in order: waits for the slot, issues one MMA per non-empty
-//                             8-pixel group (A = the slot's atoms 0,1,2 (+1 junk atom: M = 128), B = atoms 0 and 2:
-//                             N = 48), commits the slot back to the front-end, cuts the chains and publishes their
-//                             records to the drain warps.  It also allocates TMEM.
-//   Operand slot (12 KB): atom a (a = 0 code-h, 1 code-l, 2 pose: h at features 0-7, l at 8-15, rest zero) at
+//     warp 15     control   : the whole warp walks the blocks in order (uniform control flow), one elected lane issues:
+//                             waits for the slot, one MMA per non-empty 8-pixel group (A = the slot's atoms 0,1,2 (+1
+//                             ignored atom: M = 128), B = atoms 0 and 2: N = 48), commits the slot to the warp that
+//                             uses it next, cuts the chains and publishes their records to the drain warps.  It also
+//                             allocates TMEM.  This loop is serial per CTA: ~60 instructions per block.
+//   Operand slots: DFK_TC_SLOTS = 7 of 12 KB, block j uses slot j % 7 (an odd count rotates every warp through every slot;
+//   more slots cost L1 capacity the gathers want: 5 / 6 / 7 / 8 slots = 0.152 / 0.158 / 0.148 / 0.172 ms).  Atom a (a = 0 code-h, 1 code-l, 2 pose: h at features 0-7, l at 8-15, rest zero) at
 //   a * 4096; inside, K atom q (pixels 4q..4q+3) at q * 512, pixel row r at r * 128, 32-byte chunk c at (c ^ r) * 32.
 //   Accumulator rows (TMEM lanes): 0-31 code-h, 32-63 code-l, 64-71 pose-h, 72-79 pose-l; columns 0-31 code, 32-39 pose.
 //   The fp32 accumulator in TMEM adds with truncation (measured: ~ -2^-24 relative per k-step), so a chain is cut every
@@ -41,7 +44,8 @@
 //
 // The static tile->CTA assignment, the in-item tile permutation, the per-CTA partials and the wide deterministic
 // finalize are those of the fp32 kernel.  The round-1 kernel (TMA-staged tiles, operand warps transposing into a TMEM
-// A operand) and two intermediate redesigns are kept under tools/experiments/ with their measurements.
+// A operand), two intermediate redesigns and the three-term bf16 split of this kernel are kept under tools/experiments/
+// with their measurements (profiles/README.md).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -10,6 +10,10 @@
 //                          [pose_k (6) | code_k (C)] per keyframe; a pair (k0 -> k1) adds its pose0 / code0 blocks to
 //                          keyframe k0's diagonal block, pose1 to k1's, and the pose0-pose1 / pose1-code0 couplings off the
 //                          diagonal.  The buffer is what one NCCL all-reduce sums across ranks.
+//   LinearizeReprojection / LinearizeSparseGeometric
+//                          the Jacobian rows of the two sparse factors (reprojection_factor.cpp:157-269,
+//                          sparse_geometric_factor.cpp:157-271), evaluated on the device from the keyframes' GPU buffers;
+//                          the caller copies the row blocks into gtsam::VerticalBlockMatrix Ab(0..) as the reference does.
 // deepfactors_b200/factors.py is the Python mirror; tests/cpp/factor_test.cpp checks the two against each other.
 #ifndef DFK_FACTOR_H_
 #define DFK_FACTOR_H_
@@ -105,6 +109,57 @@ private:
 
 // contiguous, balanced shard of the pair list for `rank` (sizes differ by at most one): pairs shard across GPUs with
 // no data-path collective, the window buffers of the ranks are summed by one all-reduce
+// Rows of a JacobianFactor, row-major; `width` floats per row, the last one is b.
+struct SparseRows {
+  std::vector<float> rows;
+  int num_rows = 0;
+  int width = 0;
+  float total_err = 0.0f;  // ReprojectionFactor: sum of squared unweighted errors (total_err_, reprojection_factor.cpp:242)
+  int num_valid = 0;       // SparseGeometricFactor: rows that are not all zero
+  const float* row(int i) const { return rows.data() + static_cast<std::size_t>(i) * width; }
+};
+
+// ReprojectionFactor::linearize (reprojection_factor.cpp:157-269): 2 rows per match,
+// [dErr/dPose0 (6) | dErr/dPose1 (6) | dErr/dCode0 (CS) | b].  query_xy / train_xy: 2 floats per match (host);
+// prx_orig / prx_jac: the keyframe's level-0 GPU views (kf->pyr_prx_orig.GetGpuLevel(0), kf->pyr_jac.GetGpuLevel(0)).
+template <int CS, typename SE3T, typename CodeT, typename CamT, typename ImageBuffer>
+SparseRows LinearizeReprojection(DfkHandle h, const SE3T& pose0, const SE3T& pose1, const CodeT& code0, const CamT& cam,
+                                 const ImageBuffer& prx_orig, const ImageBuffer& prx_jac, int num_matches,
+                                 const float* query_xy, const float* train_xy, float huber_delta, float sigma)
+{
+  SparseRows out;
+  out.num_rows = 2 * num_matches;
+  out.width = 13 + CS;
+  out.rows.assign(static_cast<std::size_t>(out.num_rows) * out.width, 0.0f);
+  const DfkCamera c = detail::Cam(cam);
+  const DfkImage p = detail::View(prx_orig, 1), j = detail::View(prx_jac, CS);
+  detail::Check(h, dfk_reprojection_linearize(h, pose0.data(), pose1.data(), code0.data(), CS, &c, &p, &j, num_matches,
+                                              query_xy, train_xy, huber_delta, sigma, out.rows.data(), &out.total_err));
+  return out;
+}
+
+// SparseGeometricFactor::linearize (sparse_geometric_factor.cpp:157-271): 1 row per sampled point,
+// [dErr/dPose0 (6) | dErr/dPose1 (6) | dErr/dCode0 (CS) | dErr/dCode1 (CS) | b].  points_xy: 2 ints per point (host);
+// the image arguments are the two keyframes' level-0 GPU views and kf1's depth gradient (2 floats per pixel).
+template <int CS, typename SE3T, typename CodeT, typename CamT, typename ImageBuffer, typename GradBuffer>
+SparseRows LinearizeSparseGeometric(DfkHandle h, const SE3T& pose0, const SE3T& pose1, const CodeT& code0, const CodeT& code1,
+                                    const CamT& cam, const ImageBuffer& prx0_orig, const ImageBuffer& prx0_jac,
+                                    const ImageBuffer& prx1_orig, const ImageBuffer& prx1_jac, const GradBuffer& dpt_grad1,
+                                    int num_points, const int* points_xy, float huber_delta)
+{
+  SparseRows out;
+  out.num_rows = num_points;
+  out.width = 13 + 2 * CS;
+  out.rows.assign(static_cast<std::size_t>(out.num_rows) * out.width, 0.0f);
+  const DfkCamera c = detail::Cam(cam);
+  const DfkImage p0 = detail::View(prx0_orig, 1), j0 = detail::View(prx0_jac, CS), p1 = detail::View(prx1_orig, 1),
+                 j1 = detail::View(prx1_jac, CS), g1 = detail::View(dpt_grad1, 2);
+  detail::Check(h, dfk_sparse_geometric_linearize(h, pose0.data(), pose1.data(), code0.data(), code1.data(), CS, &c, &p0, &j0,
+                                                  &p1, &j1, &g1, num_points, points_xy, huber_delta, out.rows.data(),
+                                                  &out.num_valid));
+  return out;
+}
+
 inline void ShardPairs(std::size_t num_pairs, int world_size, int rank, std::size_t* begin, std::size_t* end)
 {
   *begin = (num_pairs * static_cast<std::size_t>(rank)) / static_cast<std::size_t>(world_size);

@@ -7,6 +7,36 @@
 
 #include "df/dfk_factor.h"
 
+// Compile-time check of the sparse-factor wrappers (they need a device to RUN: tests/test_gpu_parity.py drives the same
+// C entry points): stand-ins with the accessor names of vc::Image2DView / df::PinholeCamera / Sophus::SE3f / Eigen vectors.
+namespace
+{
+struct ViewStandIn {
+  const float* ptr() const { return nullptr; }
+  std::size_t pitch() const { return 0; }
+  std::size_t width() const { return 0; }
+  std::size_t height() const { return 0; }
+};
+struct CamStandIn {
+  float fx() const { return 1; }
+  float fy() const { return 1; }
+  float u0() const { return 0; }
+  float v0() const { return 0; }
+  float width() const { return 0; }
+  float height() const { return 0; }
+};
+struct VecStandIn {
+  const float* data() const { return nullptr; }
+};
+using ReprojFn = df::SparseRows (*)(DfkHandle, const VecStandIn&, const VecStandIn&, const VecStandIn&, const CamStandIn&,
+                                    const ViewStandIn&, const ViewStandIn&, int, const float*, const float*, float, float);
+using GeomFn = df::SparseRows (*)(DfkHandle, const VecStandIn&, const VecStandIn&, const VecStandIn&, const VecStandIn&,
+                                  const CamStandIn&, const ViewStandIn&, const ViewStandIn&, const ViewStandIn&,
+                                  const ViewStandIn&, const ViewStandIn&, int, const int*, float);
+volatile ReprojFn g_reproj = &df::LinearizeReprojection<8, VecStandIn, VecStandIn, CamStandIn, ViewStandIn>;
+volatile GeomFn g_geom = &df::LinearizeSparseGeometric<8, VecStandIn, VecStandIn, CamStandIn, ViewStandIn, ViewStandIn>;
+}  // namespace
+
 int main()
 {
   constexpr int CS = 8, NP = 12 + CS;

@@ -80,6 +80,8 @@ def compare_step(gpu, o32, o64, what):
 
 @pytest.mark.parametrize("w,h,cs,extra", [(160, 120, 8, 0), (160, 120, 8, 12), (320, 240, 32, 0), (320, 240, 32, 20),
                                           (640, 480, 32, 0), (200, 96, 16, 4), (202, 96, 8, 1),
+                                          # the coarse pyramid levels of the benchmark workload, on their own
+                                          (160, 120, 32, 0), (80, 60, 32, 4),
                                           # the code sizes the reference declares but cannot launch
                                           # (cu_sfmaligner.cpp:170-173,210-211); BASELINE config C=128
                                           (160, 120, 64, 0), (202, 96, 64, 1), (160, 120, 128, 4), (320, 240, 128, 0)])

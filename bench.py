@@ -604,7 +604,7 @@ def main():
     # host runs ahead of the device; coming out of a synchronize that pipeline takes a few steps to fill (0.5 - 4 ms at
     # N = 2 .. 8), which a 20-step region would charge to the steady-state rate the metric is about.  The K timed steps,
     # their collectives and the final drain are all inside [e0, e1].
-    lead_in = max(3, args.warmup)
+    lead_in = max(3, args.warmup) if world == 1 else max(8, args.warmup)   # ranks couple through collectives two steps deep
     for _ in range(lead_in):
         step()
     e0.record()
